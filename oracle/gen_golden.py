@@ -1,0 +1,149 @@
+"""Generate the golden fixtures under tests/golden/ by running the UNMODIFIED reference on CPU.
+
+Run in the build container only (it needs /root/reference, which does not exist on the GPU box):
+
+    python oracle/gen_golden.py            # writes tests/golden/*.npz
+
+The reference is imported from where it lies (nothing is copied); the only shims are a dummy
+`matplotlib` module (BigVGAN/utils.py:7-13 imports it at module scope, it is absent here) and
+an attribute-dict standing in for OmegaConf.  Weights come from
+`b200vgan.synth` (deterministic, regenerated identically by the tests), loaded into the
+reference module with `load_state_dict`; outputs are what the reference's own torch code
+computes in fp32 (and fp64 for the full forward, to show the fp32 noise floor).
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+import yaml
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_ROOT = os.environ.get("BVG_REF_ROOT", "/root/reference")
+sys.path.insert(0, os.path.join(ROOT, "index-tts-dubbing_b200"))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def import_reference():
+    mpl = types.ModuleType("matplotlib")
+    mpl.use = lambda *a, **k: None
+    pl = types.ModuleType("matplotlib.pylab")
+    mpl.pylab = pl
+    sys.modules["matplotlib"] = mpl
+    sys.modules["matplotlib.pylab"] = pl
+    sys.path.insert(0, REF_ROOT)
+    import indextts.BigVGAN.models as models
+    return models
+
+
+class H(dict):
+    __getattr__ = dict.__getitem__
+
+    def __setattr__(self, k, v):
+        self[k] = v
+
+
+def ref_generator(models, sd_np, dtype=torch.float32):
+    h = H(yaml.safe_load(open(f"{REF_ROOT}/checkpoints/config.yaml"))["bigvgan"])
+    g = models.BigVGAN(h, use_cuda_kernel=False)
+    g.remove_weight_norm()
+    g.eval()
+    missing = g.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd_np.items()}, strict=True)
+    print("load_state_dict:", missing)
+    return g.to(dtype)
+
+
+def main():
+    from b200vgan import synth
+    torch.set_grad_enabled(False)
+    torch.manual_seed(0)
+    models = import_reference()
+    from indextts.BigVGAN.alias_free_torch import Activation1d
+    from indextts.BigVGAN.alias_free_torch.filter import kaiser_sinc_filter1d
+    from indextts.BigVGAN import activations
+    os.makedirs(GOLD, exist_ok=True)
+
+    # 1. filter taps ------------------------------------------------------------------
+    taps = kaiser_sinc_filter1d(0.25, 0.3, 12).reshape(-1).numpy()
+    np.savez(os.path.join(GOLD, "kaiser_taps.npz"), taps=taps)
+
+    # 2. Activation1d(SnakeBeta, logscale) ---------------------------------------------
+    rng = np.random.default_rng(11)
+    cases = {}
+    for name, (B, C, L) in {"a": (2, 16, 50), "b": (1, 8, 1), "c": (1, 24, 7), "d": (3, 8, 301)}.items():
+        x = (1.5 * rng.standard_normal((B, C, L))).astype(np.float32)
+        la = (0.5 * rng.standard_normal(C)).astype(np.float32)
+        lb = (0.5 * rng.standard_normal(C)).astype(np.float32)
+        act = Activation1d(activation=activations.SnakeBeta(C, alpha_logscale=True))
+        act.act.alpha.data = torch.from_numpy(la)
+        act.act.beta.data = torch.from_numpy(lb)
+        y = act(torch.from_numpy(x)).numpy()
+        cases.update({f"{name}_x": x, f"{name}_alpha": la, f"{name}_beta": lb, f"{name}_y": y})
+    np.savez(os.path.join(GOLD, "activation1d.npz"), **cases)
+
+    # 3. AMPBlock1 at a small width (reference class, own synthetic weights) -------------
+    h = H(yaml.safe_load(open(f"{REF_ROOT}/checkpoints/config.yaml"))["bigvgan"])
+    h["use_cuda_kernel"] = False
+    amp = {}
+    for ks in (3, 7, 11):
+        C, L = 16, 160
+        blk = models.AMPBlock1(h, C, ks, (1, 3, 5), activation="snakebeta")
+        blk.remove_weight_norm()
+        blk.eval()
+        sd = {k: ((0.8 / (C * ks) ** 0.5) * torch.randn_like(v) if v.ndim == 3 and v.shape[-1] != 12 else
+                  (0.5 * torch.randn_like(v) if "act." in k else
+                   (0.1 * torch.randn_like(v) if k.endswith("bias") else v)))
+              for k, v in blk.state_dict().items()}
+        blk.load_state_dict(sd)
+        x = torch.randn(2, C, L)
+        y = blk(x)
+        amp.update({f"k{ks}.{k}": v.numpy() for k, v in sd.items()})
+        amp[f"k{ks}.x"] = x.numpy()
+        amp[f"k{ks}.y"] = y.numpy()
+    np.savez(os.path.join(GOLD, "ampblock1.npz"), **amp)
+
+    # 4. full generator + ECAPA with the synthetic weights --------------------------------
+    sd_np = synth.make_state_dict(seed=1234)
+    g32 = ref_generator(models, sd_np)
+    # 4a. ECAPA on two prompts (one with relative lengths)
+    mel = synth.make_mel(seed=7, Tm=60, B=2)
+    emb = g32.speaker_encoder(torch.from_numpy(mel)).numpy()
+    lens = np.array([1.0, 0.6], dtype=np.float32)
+    emb_l = g32.speaker_encoder(torch.from_numpy(mel), torch.from_numpy(lens)).numpy()
+    np.savez(os.path.join(GOLD, "ecapa.npz"), mel=mel, emb=emb, lens=lens, emb_lens=emb_l)
+
+    # 4b. tiny full forward: B=2 (shared prompt, B'=1), T=6
+    x = synth.make_latents(0, 0, 2, 6)
+    mel1 = synth.make_mel(seed=7, Tm=60, B=1)
+    wav = g32(torch.from_numpy(x), torch.from_numpy(mel1))[0].numpy()
+    g64 = ref_generator(models, sd_np, torch.float64)
+    wav64 = g64(torch.from_numpy(x).double(), torch.from_numpy(mel1).double())[0].numpy()
+    emb1 = g32.speaker_encoder(torch.from_numpy(mel1)).numpy()
+    print("tiny: amp", np.abs(wav).max(), "std", wav.std(), "fp32-vs-fp64 maxabs", np.abs(wav - wav64).max())
+    np.savez(os.path.join(GOLD, "forward_tiny.npz"), x=x, mel=mel1, emb=emb1, wav=wav,
+             wav64=wav64.astype(np.float32))
+
+    # 4c. cfg1-sized forward: B=1, T=118 (~5 s), prompt Tm=400
+    x = synth.make_latents(1, 0, 1, 118)
+    mel4 = synth.make_mel(seed=7, Tm=400, B=1)
+    emb4 = g32.speaker_encoder(torch.from_numpy(mel4)).numpy()
+    wav = g32(torch.from_numpy(x), torch.from_numpy(mel4))[0].numpy()
+    wav64 = g64(torch.from_numpy(x).double(), torch.from_numpy(mel4).double())[0].numpy()
+    print("cfg1: amp", np.abs(wav).max(), "std", wav.std(), "fp32-vs-fp64 maxabs", np.abs(wav - wav64).max())
+    np.savez_compressed(os.path.join(GOLD, "forward_cfg1.npz"), emb=emb4, wav=wav.astype(np.float32),
+                        fp32_noise=np.float32(np.abs(wav - wav64).max()))
+
+    # 5. log-mel of the reference front-end (torchaudio) on the cfg1 waveform ---------------
+    try:
+        sys.path.insert(0, REF_ROOT)
+        from indextts.utils.feature_extractors import MelSpectrogramFeatures
+        fe = MelSpectrogramFeatures()
+        m = fe(torch.from_numpy(wav[:, 0, :24000])).numpy()
+        np.savez_compressed(os.path.join(GOLD, "logmel.npz"), wav=wav[:, 0, :24000], mel=m)
+    except Exception as e:  # torchaudio missing pieces
+        print("logmel fixture skipped:", e)
+
+
+if __name__ == "__main__":
+    main()
