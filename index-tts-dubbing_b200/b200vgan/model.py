@@ -1,0 +1,324 @@
+"""Drop-in `BigVGAN` generator module backed by libb200vgan.so.
+
+Mirrors the reference's public surface for this path (reference: indextts/BigVGAN/models.py:130-260):
+
+    g = BigVGAN(h, use_cuda_kernel=True)          # infer.py:110
+    g.load_state_dict(ckpt["generator"])          # checkpoint layout (weight_g/weight_v, 1029 keys)
+    g = g.to(device); g.remove_weight_norm(); g.eval()   # infer.py:114-117
+    wav, _ = g(latent, mel_ref)                   # infer.py:458, :623   -> ([B,1,1024*T], None)
+
+The torch side only holds parameters (so state dicts round-trip in either the checkpoint layout or
+the folded layout) and device memory; every generator FLOP runs in hand-written sm_100a kernels
+behind the C ABI.  There is NO torch / CPU fallback for the generator: construction fails without
+the shared library, and forward fails without an sm_100 GPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import lib as _lib
+from .ecapa import ECAPA_TDNN
+from .synth import kaiser_filter
+
+_DT = {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16, torch.float16: _lib.F16}
+
+
+def _hget(h, k, default=None):
+    if isinstance(h, dict):
+        return h.get(k, default)
+    if hasattr(h, k):
+        return getattr(h, k)
+    try:
+        return h.get(k, default)
+    except Exception:
+        return default
+
+
+class _WNConv(nn.Module):
+    """Parameter holder for a weight-normed Conv1d / ConvTranspose1d.  State-dict keys are
+    `weight_g`, `weight_v`, `bias` until remove_weight_norm(), then `weight`, `bias`
+    (torch.nn.utils.weight_norm semantics: g has shape [dim0,1,1], norm over all dims but 0)."""
+
+    def __init__(self, shape: Tuple[int, int, int], n_bias: int):
+        super().__init__()
+        self.shape = tuple(shape)
+        self.weight_g = nn.Parameter(torch.ones(shape[0], 1, 1))
+        self.weight_v = nn.Parameter(torch.randn(*shape) * (1.0 / (shape[1] * shape[2]) ** 0.5))
+        self.bias = nn.Parameter(torch.zeros(n_bias))
+        with torch.no_grad():
+            self.weight_g.copy_(self.weight_v.flatten(1).norm(dim=1).view(-1, 1, 1))
+
+    @property
+    def folded(self) -> bool:
+        return "weight" in self._parameters and self._parameters["weight"] is not None
+
+    def effective_weight(self) -> torch.Tensor:
+        if self.folded:
+            return self.weight.detach()
+        v = self.weight_v.detach().double()
+        g = self.weight_g.detach().double()
+        nrm = v.flatten(1).norm(dim=1).view(-1, 1, 1)
+        return (g * v / nrm).float()
+
+    def remove_weight_norm(self):
+        if self.folded:
+            return
+        w = self.effective_weight()
+        del self._parameters["weight_g"]
+        del self._parameters["weight_v"]
+        self.weight = nn.Parameter(w)
+
+    def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
+        has_folded = prefix + "weight" in state_dict
+        has_wn = prefix + "weight_g" in state_dict
+        dev = self.bias.device
+        if has_folded and not self.folded:
+            del self._parameters["weight_g"]
+            del self._parameters["weight_v"]
+            self.weight = nn.Parameter(torch.zeros(*self.shape, device=dev))
+        elif has_wn and self.folded:
+            del self._parameters["weight"]
+            self.weight_g = nn.Parameter(torch.ones(self.shape[0], 1, 1, device=dev))
+            self.weight_v = nn.Parameter(torch.zeros(*self.shape, device=dev))
+        super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
+
+
+class _Filter(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.register_buffer("filter", torch.from_numpy(kaiser_filter()).view(1, 1, 12).clone())
+
+
+class _Down(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.lowpass = _Filter()
+
+
+class _SnakeBeta(nn.Module):
+    def __init__(self, ch):
+        super().__init__()
+        self.alpha = nn.Parameter(torch.zeros(ch))  # log scale (activations.py:99-102)
+        self.beta = nn.Parameter(torch.zeros(ch))
+
+
+class _Activation1d(nn.Module):
+    """Parameter holder with the reference key layout `act.{alpha,beta}`, `upsample.filter`,
+    `downsample.lowpass.filter` (alias_free_torch/act.py:9-22)."""
+
+    def __init__(self, ch):
+        super().__init__()
+        self.act = _SnakeBeta(ch)
+        self.upsample = _Filter()
+        self.downsample = _Down()
+
+
+class _AMPBlock1(nn.Module):
+    def __init__(self, ch, k, n_dil):
+        super().__init__()
+        self.convs1 = nn.ModuleList([_WNConv((ch, ch, k), ch) for _ in range(n_dil)])
+        self.convs2 = nn.ModuleList([_WNConv((ch, ch, k), ch) for _ in range(n_dil)])
+        self.activations = nn.ModuleList([_Activation1d(ch) for _ in range(2 * n_dil)])
+
+
+class BigVGAN(nn.Module):
+    def __init__(self, h, use_cuda_kernel: bool = True, precision: str = "bf16"):
+        super().__init__()
+        self.h = h
+        try:
+            h["use_cuda_kernel"] = use_cuda_kernel  # models.py:141 does the same
+        except Exception:
+            pass
+        self._cfg = _lib.make_config(h)
+        self._libh = _lib.load()            # fails loudly if the extension is missing
+        self.precision = precision
+        cfg = self._cfg
+        self.num_kernels = cfg.num_kernels
+        self.num_upsamples = cfg.num_upsamples
+        self.cond_in_each_up_layer = bool(cfg.cond_in_each_up_layer)
+        c0, nd = cfg.upsample_initial_channel, cfg.num_dilations
+        self.conv_pre = _WNConv((c0, cfg.gpt_dim, 7), c0)
+        self.ups = nn.ModuleList()
+        self.resblocks = nn.ModuleList()
+        ch = c0
+        self.hop = 1
+        for i in range(cfg.num_upsamples):
+            k, u = cfg.upsample_kernel_sizes[i], cfg.upsample_rates[i]
+            self.hop *= u
+            self.ups.append(nn.ModuleList([_WNConv((ch, ch // 2, k), ch // 2)]))
+            ch //= 2
+            for j in range(cfg.num_kernels):
+                self.resblocks.append(_AMPBlock1(ch, cfg.resblock_kernel_sizes[j], nd))
+        self.activation_post = _Activation1d(ch)
+        self.conv_post = _WNConv((1, ch, 7), 1)
+        spk = cfg.speaker_embedding_dim
+        self.speaker_encoder = ECAPA_TDNN(int(_hget(h, "num_mels", 100)), lin_neurons=spk)
+        self.cond_layer = nn.Conv1d(spk, c0, 1)
+        if self.cond_in_each_up_layer:
+            self.conds = nn.ModuleList([nn.Conv1d(spk, c0 >> (i + 1), 1) for i in range(cfg.num_upsamples)])
+        # engine state
+        self._handle = None
+        self._engine_dirty = True
+        self._plans: Dict[Tuple[Tuple[int, ...], int], C.c_void_p] = {}
+        self._workspace: Optional[torch.Tensor] = None
+        self._spk_cache: Dict[Tuple, torch.Tensor] = {}
+
+    # ---- reference surface -------------------------------------------------------------------
+    def remove_weight_norm(self):
+        """Idempotent (models.py:252-260 would raise on a second call; a drop-in may be called twice)."""
+        for m in self.modules():
+            if isinstance(m, _WNConv):
+                m.remove_weight_norm()
+        self._engine_dirty = True
+
+    def load_state_dict(self, state_dict, strict: bool = True, **kw):
+        r = super().load_state_dict(state_dict, strict=strict, **kw)
+        self._engine_dirty = True
+        self._spk_cache.clear()
+        return r
+
+    def _apply(self, fn, *a, **kw):
+        r = super()._apply(fn, *a, **kw)
+        self._engine_dirty = True
+        return r
+
+    def forward(self, x, mel_ref, lens=None):
+        """x [B,T,gpt_dim] latents, mel_ref [B',Tm,num_mels] -> (wav [B,1,T*hop] fp32, None)."""
+        emb = self.speaker_embedding(mel_ref, lens)
+        if emb.shape[0] == 2 * x.shape[0]:
+            raise RuntimeError("contrastive branch (B' == 2B, models.py:205-209) is training-only")
+        return self.forward_with_embedding(x, emb), None
+
+    # ---- extensions --------------------------------------------------------------------------
+    @torch.no_grad()
+    def speaker_embedding(self, mel_ref, lens=None, cache_key=None):
+        """ECAPA embedding [B',1,512]; pass `cache_key` (e.g. the prompt path) to reuse it."""
+        if cache_key is not None and cache_key in self._spk_cache:
+            return self._spk_cache[cache_key]
+        dev = self.conv_pre.bias.device
+        emb = self.speaker_encoder(mel_ref.to(dev), None if lens is None else lens.to(dev)).float().contiguous()
+        if cache_key is not None:
+            self._spk_cache[cache_key] = emb
+        return emb
+
+    @torch.no_grad()
+    def forward_with_embedding(self, x, emb, x_lens: Optional[Sequence[int]] = None):
+        """Decode with a precomputed speaker embedding.  `x_lens` (host ints, latent frames per
+        batch item) enables exact variable-length batches: item b is decoded as if alone."""
+        if not x.is_cuda:
+            raise _lib.BvgError("b200vgan has no CPU path: latents must live on a CUDA (sm_100) device")
+        if x.dtype not in _DT:
+            x = x.float()
+        x = x.contiguous()
+        B, T, D = x.shape
+        if D != self._cfg.gpt_dim:
+            raise _lib.BvgError(f"latent width {D} != gpt_dim {self._cfg.gpt_dim}")
+        frames = tuple(int(v) for v in x_lens) if x_lens is not None else (T,) * B
+        if len(frames) != B or max(frames) != T:
+            raise _lib.BvgError("x_lens must have B entries and max(x_lens) == x.shape[1]")
+        emb = emb.to(device=x.device, dtype=torch.float32).contiguous()
+        if emb.shape[0] not in (1, B):
+            raise _lib.BvgError("speaker embedding batch must be 1 or B")
+        with torch.cuda.device(x.device):
+            self._ensure_engine(x.device)
+            mode = _lib.MODE_FP32 if self.precision == "fp32" else _lib.MODE_BF16
+            plan = self._plan(frames, mode)
+            ws = self._ensure_workspace(int(self._libh.bvg_plan_workspace_bytes(plan)), x.device)
+            wav = torch.empty(B, 1, T * self.hop, device=x.device, dtype=torch.float32)
+            stream = torch.cuda.current_stream(x.device).cuda_stream
+            _lib.check(self._libh.bvg_forward(self._handle, plan, x.data_ptr(), _DT[x.dtype], emb.data_ptr(),
+                                              emb.shape[0], wav.data_ptr(), ws.data_ptr(), ws.numel(), stream))
+        return wav
+
+    def num_launches(self, frames: Sequence[int]) -> int:
+        mode = _lib.MODE_FP32 if self.precision == "fp32" else _lib.MODE_BF16
+        return int(self._libh.bvg_plan_num_launches(self._plan(tuple(int(f) for f in frames), mode)))
+
+    PROFILE_CLASSES = ("activation1d", "conv_tcgen05", "conv_cuda_core", "other")
+
+    def profile_enable(self, on: bool = True):
+        """Bracket every kernel launch of forward with CUDA events (see bvg_profile_read)."""
+        if self._handle is None:
+            raise _lib.BvgError("profile_enable: run one forward first (engine not built)")
+        _lib.check(self._libh.bvg_profile_enable(self._handle, 1 if on else 0))
+
+    def profile_read(self) -> Dict[str, Dict[str, float]]:
+        ms, fl, by = (C.c_double * 4)(), (C.c_double * 4)(), (C.c_double * 4)()
+        n = (C.c_int64 * 4)()
+        _lib.check(self._libh.bvg_profile_read(self._handle, ms, fl, by, n))
+        return {c: {"ms": ms[i], "flops": fl[i], "bytes": by[i], "launches": int(n[i])}
+                for i, c in enumerate(self.PROFILE_CLASSES)}
+
+    # ---- engine plumbing ---------------------------------------------------------------------
+    def folded_state(self) -> Dict[str, torch.Tensor]:
+        """Generator parameters in the folded layout, by reference state-dict name."""
+        out = {}
+        for name, m in self.named_modules():
+            if isinstance(m, _WNConv):
+                out[name + ".weight"] = m.effective_weight()
+                out[name + ".bias"] = m.bias.detach()
+            elif isinstance(m, _SnakeBeta):
+                out[name + ".alpha"] = m.alpha.detach()
+                out[name + ".beta"] = m.beta.detach()
+        out["cond_layer.weight"] = self.cond_layer.weight.detach()
+        out["cond_layer.bias"] = self.cond_layer.bias.detach()
+        if self.cond_in_each_up_layer:
+            for i, c in enumerate(self.conds):
+                out[f"conds.{i}.weight"] = c.weight.detach()
+                out[f"conds.{i}.bias"] = c.bias.detach()
+        return out
+
+    def _ensure_engine(self, device):
+        if self._handle is not None and not self._engine_dirty:
+            return
+        if self._handle is None:
+            hd = C.c_void_p()
+            _lib.check(self._libh.bvg_create(C.byref(self._cfg), C.byref(hd)))
+            self._handle = hd
+        stream = torch.cuda.current_stream(device).cuda_stream
+        keep = []
+        for name, t in self.folded_state().items():
+            t = t.to(device=device, dtype=torch.float32).contiguous()
+            keep.append(t)
+            shape = (C.c_int64 * t.dim())(*t.shape)
+            _lib.check(self._libh.bvg_set_weight(self._handle, name.encode(), t.data_ptr(), shape, t.dim(), 1, stream))
+        _lib.check(self._libh.bvg_finalize(self._handle, stream))
+        del keep
+        self._engine_dirty = False
+
+    def _plan(self, frames: Tuple[int, ...], mode: int):
+        key = (frames, mode)
+        p = self._plans.get(key)
+        if p is None:
+            if len(self._plans) >= 64:          # bound the cache for long dubbing jobs
+                k0 = next(iter(self._plans))
+                self._libh.bvg_plan_destroy(self._plans.pop(k0))
+            p = C.c_void_p()
+            arr = (C.c_int32 * len(frames))(*frames)
+            _lib.check(self._libh.bvg_plan_create(self._handle, len(frames), arr, mode, C.byref(p)))
+            self._plans[key] = p
+        return p
+
+    def _ensure_workspace(self, nbytes: int, device) -> torch.Tensor:
+        ws = self._workspace
+        if ws is None or ws.numel() < nbytes or ws.device != device:
+            self._workspace = None
+            ws = torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=device)
+            self._workspace = ws
+            if self._handle is not None:   # the old address may come back with stale guard rows
+                _lib.check(self._libh.bvg_workspace_reset(self._handle))
+        return ws
+
+    def __del__(self):
+        try:
+            for p in self._plans.values():
+                self._libh.bvg_plan_destroy(p)
+            if self._handle is not None:
+                self._libh.bvg_destroy(self._handle)
+        except Exception:
+            pass

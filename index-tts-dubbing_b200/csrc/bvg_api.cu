@@ -1,0 +1,691 @@
+// C ABI of libb200vgan.so: generator handle, per-geometry plan, the forward launch sequence and
+// the per-op entry points.  See include/b200vgan.h for the contract of every function.
+//
+// The launch sequence in bvg_forward mirrors the reference's BigVGAN.forward
+// (indextts/BigVGAN/models.py:210-250) and AMPBlock1.forward (models.py:65-74) with
+//   * the speaker conditioning  x + cond(spk)  (models.py:226, :233-234) folded into a per-segment
+//     bias of conv_pre / the up-convolutions,
+//   * the residual add  xt + x  (models.py:72) and the resblock mean  xs / 3  (models.py:237-243)
+//     folded into the epilogue of each block's last convolution.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/b200vgan.h"
+#include "bvg_common.cuh"
+#include "bvg_misc.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return 1;
+}
+
+#define CK(expr)                                                                                   \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess) return fail("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+  } while (0)
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+struct ConvLayer {
+  bool transposed = false;
+  int Cin = 0, Cout = 0, k = 0, d = 1, u = 1, p = 0;
+  int ntaps = 0, N = 0, q_extra = 0;
+  int tap_off[BVG_MAX_TAPS] = {0};
+  float* w_raw = nullptr;   // reference layout, fp32 (device)
+  float* bias = nullptr;    // [Cout]
+  float* w_tap = nullptr;   // [ntaps][Cin][N] fp32
+  void* w_umma = nullptr;   // bf16 UMMA shared-memory images
+  void setup() {
+    if (!transposed) {
+      ntaps = k; N = Cout; u = 1; p = 0; q_extra = 0;
+      for (int j = 0; j < k; ++j) tap_off[j] = (j - (k - 1) / 2) * d;
+    } else {
+      ntaps = k / u; N = u * Cout; p = (k - u) / 2; q_extra = p > 0 ? 1 : 0;
+      for (int m = 0; m < ntaps; ++m) tap_off[m] = -m;
+    }
+  }
+};
+
+struct ActLayer {
+  int C = 0;
+  float *la = nullptr, *lb = nullptr, *alpha = nullptr, *inv_beta = nullptr;
+};
+
+struct CondLayer {
+  int C = 0;
+  float *w = nullptr, *b = nullptr;
+};
+
+struct ParamSlot {
+  float** dst;
+  std::vector<int64_t> shape;
+  bool set = false;
+};
+
+enum { PROF_ACT = 0, PROF_CONV_TC = 1, PROF_CONV_CC = 2, PROF_OTHER = 3, PROF_NCLS = 4 };
+struct ProfRec {
+  cudaEvent_t e0, e1;
+  int cls;
+  double flops, bytes;
+};
+
+}  // namespace
+
+struct bvg_handle {
+  bvg_config cfg{};
+  int device = 0;
+  int hop = 1;
+  int nups = 0, nk = 0, nd = 0;
+  ConvLayer conv_pre, conv_post;
+  std::vector<ConvLayer> ups;
+  std::vector<ConvLayer> c1, c2;   // [(stage*nk + j)*nd + m]
+  std::vector<ActLayer> acts;      // [(stage*nk + j)*2*nd + a]
+  ActLayer act_post;
+  CondLayer cond_pre;
+  std::vector<CondLayer> conds;
+  std::map<std::string, ParamSlot> params;
+  std::vector<void*> owned;
+  std::map<const void*, uint64_t> ws_owner;   // workspace -> uid of the plan whose guard rows it holds
+  bool finalized = false;
+  // optional per-launch CUDA-event timing (bench.py's roofline numbers)
+  bool prof_on = false;
+  std::vector<ProfRec> prof;
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_used = 0;
+};
+
+namespace {
+// Records a CUDA event pair around the launches issued inside its scope (only when profiling is on).
+struct ProfScope {
+  bvg_handle* h;
+  cudaStream_t s;
+  cudaEvent_t e1 = nullptr;
+  ProfScope(bvg_handle* h_, cudaStream_t s_, int cls, double flops, double bytes) : h(h_), s(s_) {
+    if (!h->prof_on) return;
+    while (h->ev_pool.size() < h->ev_used + 2) {
+      cudaEvent_t e;
+      if (cudaEventCreate(&e) != cudaSuccess) return;
+      h->ev_pool.push_back(e);
+    }
+    cudaEvent_t e0 = h->ev_pool[h->ev_used++];
+    e1 = h->ev_pool[h->ev_used++];
+    cudaEventRecord(e0, s);
+    h->prof.push_back(ProfRec{e0, e1, cls, flops, bytes});
+  }
+  ~ProfScope() {
+    if (e1) cudaEventRecord(e1, s);
+  }
+};
+}  // namespace
+
+struct bvg_plan {
+  bvg_handle* h = nullptr;
+  int B = 0, mode = 0, dtype = 0, esize = 4;
+  std::vector<int> frames;
+  int max_frames = 0;
+  // geometry: index 0 = latent rate (pre), 1.. = after up-conv i-1
+  std::vector<int> R, maxlen, C;
+  std::vector<long long> sumlen;   // valid rows over all segments, per geometry
+  SegDesc* seg_dev = nullptr;   // [(nups+1)][B]
+  size_t ws_bytes = 0;
+  size_t off_lat = 0, off_pre = 0, off_bias = 0;
+  std::vector<size_t> off_U, off_X, off_A, off_Y, off_XS;
+  int bias_stride = 0;
+  std::vector<int> bias_off;    // per cond layer (0 = pre, 1.. = ups)
+  uint64_t uid = 0;
+  int num_launches = 0;
+};
+
+namespace {
+
+int dev_alloc(bvg_handle* h, void** p, size_t bytes) {
+  CK(cudaMalloc(p, bytes ? bytes : 4));
+  h->owned.push_back(*p);
+  return 0;
+}
+
+void add_param(bvg_handle* h, const std::string& name, float** dst, std::vector<int64_t> shape) {
+  ParamSlot s;
+  s.dst = dst;
+  s.shape = std::move(shape);
+  h->params[name] = s;
+}
+
+void add_conv_params(bvg_handle* h, const std::string& name, ConvLayer& L) {
+  if (L.transposed) add_param(h, name + ".weight", &L.w_raw, {L.Cin, L.Cout, L.k});
+  else add_param(h, name + ".weight", &L.w_raw, {L.Cout, L.Cin, L.k});
+  add_param(h, name + ".bias", &L.bias, {L.Cout});
+}
+
+ConvArgs make_conv_args(const ConvLayer& L, const bvg_plan* p, int gin, int gout, const void* x, void* y,
+                        const void* res, const float* bias, int bias_bstride, float scale, int accumulate,
+                        bool umma) {
+  ConvArgs a{};
+  a.x = x; a.y = y; a.res = res;
+  a.w = umma ? (const void*)L.w_umma : (const void*)L.w_tap;
+  a.bias = bias; a.bias_bstride = bias_bstride;
+  a.seg_in = p->seg_dev + (size_t)gin * p->B;
+  a.seg_out = p->seg_dev + (size_t)gout * p->B;
+  a.Rx = p->R[gin]; a.Ry = p->R[gout];
+  a.Cin = L.Cin; a.Cout = L.Cout; a.ntaps = L.ntaps;
+  for (int j = 0; j < L.ntaps; ++j) a.tap_off[j] = L.tap_off[j];
+  a.u = L.u; a.p = L.p; a.q_extra = L.q_extra;
+  a.B = p->B; a.max_q = p->maxlen[gin] + L.q_extra;
+  a.out_scale = scale; a.accumulate = accumulate;
+  return a;
+}
+
+int run_conv(const ConvLayer& L, const bvg_plan* p, int gin, int gout, const void* x, void* y, const void* res,
+             const float* bias, int bias_bstride, float scale, int accumulate, cudaStream_t s) {
+  // algorithmic work of this launch: 2 * Cin * taps * N MACs per input row (valid rows only)
+  const double flops = 2.0 * L.Cin * L.ntaps * L.N * (double)p->sumlen[gin];
+  const double bytes = ((double)L.Cin * p->sumlen[gin] + (double)L.Cout * p->sumlen[gout] * (res ? 2 : 1)) * p->esize;
+  if (p->mode == BVG_MODE_BF16 && L.w_umma) {
+    ConvArgs a = make_conv_args(L, p, gin, gout, x, y, res, bias, bias_bstride, scale, accumulate, true);
+    if (conv_umma_supported(a)) {
+      ProfScope ps(p->h, s, PROF_CONV_TC, flops, bytes);
+      CK(launch_conv_umma(a, s));
+      return 0;
+    }
+  }
+  ConvArgs a = make_conv_args(L, p, gin, gout, x, y, res, bias, bias_bstride, scale, accumulate, false);
+  ProfScope ps(p->h, s, PROF_CONV_CC, flops, bytes);
+  CK(launch_conv_simt(a, p->dtype, s));
+  return 0;
+}
+
+int run_act(const ActLayer& A, const bvg_plan* p, int g, const void* x, void* y, cudaStream_t s) {
+  ActArgs aa{x, y, A.alpha, A.inv_beta, p->seg_dev + (size_t)g * p->B, p->R[g], p->C[g], p->B, p->maxlen[g]};
+  // algorithmic bytes of a standalone Activation1d launch: read + write of every valid element
+  const double bytes = 2.0 * p->C[g] * (double)p->sumlen[g] * p->esize;
+  ProfScope ps(p->h, s, PROF_ACT, 0.0, bytes);
+  CK(launch_act_c8(aa, p->dtype, p->mode == BVG_MODE_FP32, s));
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* bvg_last_error(void) { return g_err.c_str(); }
+int bvg_version(void) { return 100; }
+
+int bvg_device_check(void) {
+  int dev = 0, n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) return fail("no CUDA device: b200vgan has no CPU fallback (%s)", cudaGetErrorString(e));
+  CK(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10) return fail("device %d is sm_%d%d; b200vgan is built for sm_100a only", dev, prop.major, prop.minor);
+  return 0;
+}
+
+int bvg_create(const bvg_config* cfg, bvg_handle** out) {
+  if (!cfg || !out) return fail("bvg_create: null argument");
+  if (bvg_device_check()) return 1;
+  const int nups = cfg->num_upsamples, nk = cfg->num_kernels, nd = cfg->num_dilations;
+  if (nups < 1 || nups > BVG_MAX_UPS || nk < 1 || nk > BVG_MAX_KERNELS || nd < 1 || nd > BVG_MAX_DILATIONS)
+    return fail("bvg_create: unsupported architecture sizes");
+  if (cfg->gpt_dim % 8 || cfg->upsample_initial_channel % (8 << nups))
+    return fail("bvg_create: channel counts must stay multiples of 8 at every stage");
+  bvg_handle* h = new bvg_handle();
+  h->cfg = *cfg;
+  CK(cudaGetDevice(&h->device));
+  h->nups = nups; h->nk = nk; h->nd = nd;
+  const int C0 = cfg->upsample_initial_channel, D = cfg->speaker_embedding_dim;
+
+  h->conv_pre.Cin = cfg->gpt_dim; h->conv_pre.Cout = C0; h->conv_pre.k = 7; h->conv_pre.setup();
+  add_conv_params(h, "conv_pre", h->conv_pre);
+  h->cond_pre.C = C0;
+  add_param(h, "cond_layer.weight", &h->cond_pre.w, {C0, D, 1});
+  add_param(h, "cond_layer.bias", &h->cond_pre.b, {C0});
+
+  h->ups.resize(nups); h->conds.resize(nups);
+  h->c1.resize((size_t)nups * nk * nd); h->c2.resize((size_t)nups * nk * nd);
+  h->acts.resize((size_t)nups * nk * 2 * nd);
+  h->hop = 1;
+  int ch = C0;
+  for (int i = 0; i < nups; ++i) {
+    const int u = cfg->upsample_rates[i], k = cfg->upsample_kernel_sizes[i];
+    if (k % u || (k - u) % 2) { delete h; return fail("bvg_create: upsample (k=%d,u=%d) unsupported", k, u); }
+    h->hop *= u;
+    ConvLayer& U = h->ups[i];
+    U.transposed = true; U.Cin = ch; U.Cout = ch / 2; U.k = k; U.u = u; U.setup();
+    ch /= 2;
+    char nm[128];
+    snprintf(nm, sizeof nm, "ups.%d.0", i);
+    add_conv_params(h, nm, U);
+    if (cfg->cond_in_each_up_layer) {
+      h->conds[i].C = ch;
+      snprintf(nm, sizeof nm, "conds.%d.weight", i);
+      add_param(h, nm, &h->conds[i].w, {ch, D, 1});
+      snprintf(nm, sizeof nm, "conds.%d.bias", i);
+      add_param(h, nm, &h->conds[i].b, {ch});
+    }
+    for (int j = 0; j < nk; ++j) {
+      const int rb = i * nk + j, ks = cfg->resblock_kernel_sizes[j];
+      if (ks > BVG_MAX_TAPS || !(ks & 1)) { delete h; return fail("bvg_create: resblock kernel %d unsupported", ks); }
+      for (int m = 0; m < nd; ++m) {
+        ConvLayer& A = h->c1[(size_t)rb * nd + m];
+        A.Cin = A.Cout = ch; A.k = ks; A.d = cfg->resblock_dilation_sizes[j][m]; A.setup();
+        ConvLayer& Bc = h->c2[(size_t)rb * nd + m];
+        Bc.Cin = Bc.Cout = ch; Bc.k = ks; Bc.d = 1; Bc.setup();
+        if ((ks - 1) / 2 * A.d > BVG_GUARD - 6) { delete h; return fail("bvg_create: conv halo exceeds guard rows"); }
+        snprintf(nm, sizeof nm, "resblocks.%d.convs1.%d", rb, m);
+        add_conv_params(h, nm, A);
+        snprintf(nm, sizeof nm, "resblocks.%d.convs2.%d", rb, m);
+        add_conv_params(h, nm, Bc);
+      }
+      for (int a = 0; a < 2 * nd; ++a) {
+        ActLayer& AL = h->acts[(size_t)rb * 2 * nd + a];
+        AL.C = ch;
+        snprintf(nm, sizeof nm, "resblocks.%d.activations.%d.act.alpha", rb, a);
+        add_param(h, nm, &AL.la, {ch});
+        snprintf(nm, sizeof nm, "resblocks.%d.activations.%d.act.beta", rb, a);
+        add_param(h, nm, &AL.lb, {ch});
+      }
+    }
+  }
+  h->act_post.C = ch;
+  add_param(h, "activation_post.act.alpha", &h->act_post.la, {ch});
+  add_param(h, "activation_post.act.beta", &h->act_post.lb, {ch});
+  h->conv_post.Cin = ch; h->conv_post.Cout = 1; h->conv_post.k = 7; h->conv_post.setup();
+  add_conv_params(h, "conv_post", h->conv_post);
+  if (ch > 64) { delete h; return fail("bvg_create: conv_post supports at most 64 input channels"); }
+  *out = h;
+  return 0;
+}
+
+void bvg_destroy(bvg_handle* h) {
+  if (!h) return;
+  for (void* p : h->owned) cudaFree(p);
+  for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
+  delete h;
+}
+
+int bvg_set_weight(bvg_handle* h, const char* name, const float* data, const int64_t* shape, int32_t ndim,
+                   int32_t is_device, void* stream) {
+  if (!h || !name || !data) return fail("bvg_set_weight: null argument");
+  auto it = h->params.find(name);
+  if (it == h->params.end()) return fail("bvg_set_weight: unknown parameter '%s'", name);
+  ParamSlot& s = it->second;
+  size_t n = 1;
+  bool ok = (size_t)ndim == s.shape.size();
+  for (int i = 0; ok && i < ndim; ++i) ok = shape[i] == s.shape[i];
+  if (!ok) {
+    std::string want, got;
+    for (auto v : s.shape) want += std::to_string(v) + ",";
+    for (int i = 0; i < ndim; ++i) got += std::to_string(shape[i]) + ",";
+    return fail("bvg_set_weight: '%s' expects shape [%s] got [%s]", name, want.c_str(), got.c_str());
+  }
+  for (auto v : s.shape) n *= (size_t)v;
+  if (!*s.dst) {
+    void* p = nullptr;
+    if (dev_alloc(h, &p, n * sizeof(float))) return 1;
+    *s.dst = (float*)p;
+  }
+  CK(cudaMemcpyAsync(*s.dst, data, n * sizeof(float), is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                     (cudaStream_t)stream));
+  if (!is_device) CK(cudaStreamSynchronize((cudaStream_t)stream));
+  s.set = true;
+  h->finalized = false;
+  return 0;
+}
+
+static int finalize_conv(bvg_handle* h, ConvLayer& L, cudaStream_t s, bool want_umma) {
+  size_t n = (size_t)L.Cin * L.Cout * L.k;
+  if (!L.w_tap) {
+    void* p = nullptr;
+    if (dev_alloc(h, &p, n * sizeof(float))) return 1;
+    L.w_tap = (float*)p;
+  }
+  if (L.transposed) CK(launch_repack_convt(L.w_raw, L.w_tap, L.Cin, L.Cout, L.k, L.u, s));
+  else CK(launch_repack_conv(L.w_raw, L.w_tap, L.Cout, L.Cin, L.k, s));
+  if (want_umma) {
+    size_t bytes = umma_weight_image_bytes(L.ntaps, L.Cin, L.N);
+    if (bytes) {
+      if (!L.w_umma) {
+        if (dev_alloc(h, &L.w_umma, bytes)) return 1;
+      }
+      CK(launch_repack_umma(L.w_tap, L.w_umma, L.ntaps, L.Cin, L.N, s));
+    }
+  }
+  return 0;
+}
+
+static int finalize_act(bvg_handle* h, ActLayer& A, cudaStream_t s) {
+  if (!A.alpha) {
+    void* p = nullptr;
+    if (dev_alloc(h, &p, 2 * (size_t)A.C * sizeof(float))) return 1;
+    A.alpha = (float*)p;
+    A.inv_beta = A.alpha + A.C;
+  }
+  CK(launch_snake_params(A.la, A.lb, A.alpha, A.inv_beta, A.C, s));
+  return 0;
+}
+
+int bvg_finalize(bvg_handle* h, void* stream) {
+  if (!h) return fail("bvg_finalize: null handle");
+  cudaStream_t s = (cudaStream_t)stream;
+  for (auto& kv : h->params)
+    if (!kv.second.set) return fail("bvg_finalize: parameter '%s' was never set", kv.first.c_str());
+  if (finalize_conv(h, h->conv_pre, s, true)) return 1;
+  for (auto& L : h->ups) if (finalize_conv(h, L, s, true)) return 1;
+  for (auto& L : h->c1) if (finalize_conv(h, L, s, true)) return 1;
+  for (auto& L : h->c2) if (finalize_conv(h, L, s, true)) return 1;
+  for (auto& A : h->acts) if (finalize_act(h, A, s)) return 1;
+  if (finalize_act(h, h->act_post, s)) return 1;
+  CK(cudaStreamSynchronize(s));
+  h->finalized = true;
+  return 0;
+}
+
+int bvg_plan_create(bvg_handle* h, int32_t B, const int32_t* frames, int32_t mode, bvg_plan** out) {
+  if (!h || !frames || !out || B < 1) return fail("bvg_plan_create: bad argument");
+  if (mode != BVG_MODE_FP32 && mode != BVG_MODE_BF16) return fail("bvg_plan_create: unknown mode %d", mode);
+  static uint64_t next_uid = 1;
+  bvg_plan* p = new bvg_plan();
+  p->uid = next_uid++;
+  p->h = h; p->B = B; p->mode = mode;
+  p->dtype = mode == BVG_MODE_FP32 ? 0 : 1;
+  p->esize = p->dtype == 0 ? 4 : 2;
+  p->frames.assign(frames, frames + B);
+  const int ng = h->nups + 1;
+  std::vector<SegDesc> seg((size_t)ng * B);
+  p->R.resize(ng); p->maxlen.resize(ng); p->C.resize(ng); p->sumlen.assign(ng, 0);
+  int mult = 1;
+  for (int g = 0; g < ng; ++g) {
+    if (g > 0) mult *= h->cfg.upsample_rates[g - 1];
+    p->C[g] = g == 0 ? h->cfg.upsample_initial_channel : h->cfg.upsample_initial_channel >> g;
+    long long row = BVG_GUARD;
+    int mx = 0;
+    for (int b = 0; b < B; ++b) {
+      if (frames[b] < 1) { delete p; return fail("bvg_plan_create: segment %d has %d frames", b, frames[b]); }
+      int len = frames[b] * mult;
+      seg[(size_t)g * B + b] = SegDesc{(int)row, len};
+      row += len + BVG_GUARD;
+      mx = len > mx ? len : mx;
+      p->sumlen[g] += len;
+    }
+    row += BVG_TAIL_SLACK;
+    if (row > 0x3fffffff) { delete p; return fail("bvg_plan_create: batch too long"); }
+    p->R[g] = (int)row;
+    p->maxlen[g] = mx;
+  }
+  p->max_frames = p->maxlen[0];
+  if (cudaMalloc(&p->seg_dev, seg.size() * sizeof(SegDesc)) != cudaSuccess ||
+      cudaMemcpy(p->seg_dev, seg.data(), seg.size() * sizeof(SegDesc), cudaMemcpyHostToDevice) != cudaSuccess) {
+    delete p;
+    return fail("bvg_plan_create: segment table upload failed");
+  }
+  // workspace carve-up
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+  const size_t es = p->esize;
+  p->off_lat = take((size_t)h->cfg.gpt_dim * p->R[0] * es);
+  p->off_pre = take((size_t)p->C[0] * p->R[0] * es);
+  p->off_U.resize(ng); p->off_X.resize(ng); p->off_A.resize(ng); p->off_Y.resize(ng); p->off_XS.resize(ng);
+  for (int g = 1; g < ng; ++g) {
+    size_t bytes = (size_t)p->C[g] * p->R[g] * es;
+    p->off_U[g] = take(bytes); p->off_X[g] = take(bytes); p->off_A[g] = take(bytes);
+    p->off_Y[g] = take(bytes); p->off_XS[g] = take(bytes);
+  }
+  p->bias_off.resize(ng);
+  int bo = 0;
+  for (int g = 0; g < ng; ++g) { p->bias_off[g] = bo; bo += p->C[g]; }
+  p->bias_stride = bo;
+  p->off_bias = take((size_t)B * bo * sizeof(float));
+  p->ws_bytes = off;
+  p->num_launches = 1 + ng + 1 + h->nups * (1 + h->nk * h->nd * 4) + 2;
+  *out = p;
+  return 0;
+}
+
+void bvg_plan_destroy(bvg_plan* p) {
+  if (!p) return;
+  if (p->seg_dev) cudaFree(p->seg_dev);
+  delete p;
+}
+size_t bvg_plan_workspace_bytes(const bvg_plan* p) { return p ? p->ws_bytes : 0; }
+int32_t bvg_plan_max_frames(const bvg_plan* p) { return p ? p->max_frames : 0; }
+int32_t bvg_plan_num_launches(const bvg_plan* p) { return p ? p->num_launches : 0; }
+
+int bvg_forward(bvg_handle* h, bvg_plan* p, const void* latent, int32_t latent_dtype, const float* spk_emb,
+                int32_t spk_batch, float* wav, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!h || !p || !latent || !spk_emb || !wav || !workspace) return fail("bvg_forward: null argument");
+  if (!h->finalized) return fail("bvg_forward: call bvg_finalize first");
+  if (p->h != h) return fail("bvg_forward: plan belongs to another handle");
+  if (workspace_bytes < p->ws_bytes) return fail("bvg_forward: workspace too small (%zu < %zu)", workspace_bytes, p->ws_bytes);
+  if (spk_batch != 1 && spk_batch != p->B) return fail("bvg_forward: spk_batch must be 1 or B");
+  if (latent_dtype < 0 || latent_dtype > 2) return fail("bvg_forward: bad latent dtype");
+  cudaStream_t s = (cudaStream_t)stream;
+  char* ws = (char*)workspace;
+  const int B = p->B, ng = h->nups + 1, dt = p->dtype;
+  // Guard rows (between / around segments) must read as zero.  Kernels never write them, so they
+  // are cleared only when this workspace was last laid out for a different plan.
+  {
+    auto it = h->ws_owner.find(workspace);
+    if (it == h->ws_owner.end() || it->second != p->uid) {
+      CK(launch_zero_guards(ws + p->off_lat, p->esize, p->seg_dev, B, h->cfg.gpt_dim, p->R[0], s));
+      CK(launch_zero_guards(ws + p->off_pre, p->esize, p->seg_dev, B, p->C[0], p->R[0], s));
+      for (int g = 1; g < ng; ++g) {
+        const SegDesc* sg = p->seg_dev + (size_t)g * B;
+        const size_t offs[5] = {p->off_U[g], p->off_X[g], p->off_A[g], p->off_Y[g], p->off_XS[g]};
+        for (size_t o : offs) CK(launch_zero_guards(ws + o, p->esize, sg, B, p->C[g], p->R[g], s));
+      }
+      h->ws_owner[workspace] = p->uid;
+    }
+  }
+  const SegDesc* seg0 = p->seg_dev;
+  float* biasb = (float*)(ws + p->off_bias);
+  const int D = h->cfg.speaker_embedding_dim;
+  {
+  ProfScope ps(h, s, PROF_OTHER, 0.0, (double)h->cfg.gpt_dim * p->sumlen[0] * (4.0 + p->esize));
+  CK(launch_pack_latent(latent, latent_dtype, ws + p->off_lat, dt, seg0, B, p->max_frames, h->cfg.gpt_dim, p->R[0], s));
+  // speaker conditioning folded into per-segment biases
+  CK(launch_cond_bias(h->conv_pre.bias, h->cond_pre.w, h->cond_pre.b, spk_emb, biasb + p->bias_off[0], p->C[0], D, B,
+                      spk_batch, p->bias_stride, s));
+  for (int g = 1; g < ng; ++g) {
+    const CondLayer& c = h->conds[g - 1];
+    CK(launch_cond_bias(h->ups[g - 1].bias, c.w, c.b, spk_emb, biasb + p->bias_off[g], p->C[g], D, B, spk_batch,
+                        p->bias_stride, s));
+  }
+  }
+  // conv_pre (models.py:224-226)
+  if (run_conv(h->conv_pre, p, 0, 0, ws + p->off_lat, ws + p->off_pre, nullptr, biasb + p->bias_off[0], p->bias_stride,
+               1.f, 0, s)) return 1;
+  const void* stage_in = ws + p->off_pre;
+  for (int g = 1; g < ng; ++g) {
+    const int i = g - 1;
+    char *U = ws + p->off_U[g], *X = ws + p->off_X[g], *A = ws + p->off_A[g], *Y = ws + p->off_Y[g],
+         *XS = ws + p->off_XS[g];
+    // up-convolution + conditioning (models.py:230-234)
+    if (run_conv(h->ups[i], p, g - 1, g, stage_in, U, nullptr, biasb + p->bias_off[g], p->bias_stride, 1.f, 0, s))
+      return 1;
+    for (int j = 0; j < h->nk; ++j) {          // AMP blocks (models.py:237-243)
+      const int rb = i * h->nk + j;
+      for (int m = 0; m < h->nd; ++m) {        // AMPBlock1.forward (models.py:65-74)
+        const char* xin = m == 0 ? U : X;
+        const ActLayer& a1 = h->acts[(size_t)rb * 2 * h->nd + 2 * m];
+        const ActLayer& a2 = h->acts[(size_t)rb * 2 * h->nd + 2 * m + 1];
+        if (run_act(a1, p, g, xin, A, s)) return 1;
+        const ConvLayer& c1 = h->c1[(size_t)rb * h->nd + m];
+        if (run_conv(c1, p, g, g, A, Y, nullptr, c1.bias, 0, 1.f, 0, s)) return 1;
+        if (run_act(a2, p, g, Y, A, s)) return 1;
+        const ConvLayer& c2 = h->c2[(size_t)rb * h->nd + m];
+        const bool last = m == h->nd - 1;
+        if (run_conv(c2, p, g, g, A, last ? XS : X, xin, c2.bias, 0, last ? 1.f / h->nk : 1.f, last && j > 0, s))
+          return 1;
+      }
+    }
+    stage_in = XS;
+  }
+  // activation_post -> conv_post -> tanh (models.py:246-248)
+  {
+    const int g = ng - 1;
+    const SegDesc* seg = p->seg_dev + (size_t)g * B;
+    if (run_act(h->act_post, p, g, stage_in, ws + p->off_A[g], s)) return 1;
+    ProfScope ps(h, s, PROF_OTHER, 0.0, ((double)p->C[g] * p->esize + 4.0) * (double)p->sumlen[g]);
+    CK(launch_conv_post_tanh(ws + p->off_A[g], dt, h->conv_post.w_raw, h->conv_post.bias, wav, seg, B, p->C[g], p->R[g],
+                             p->max_frames * h->hop, s));
+  }
+  return 0;
+}
+
+int bvg_profile_enable(bvg_handle* h, int32_t on) {
+  if (!h) return fail("bvg_profile_enable: null handle");
+  h->prof_on = on != 0;
+  return 0;
+}
+
+int bvg_profile_read(bvg_handle* h, double* ms, double* flops, double* bytes, int64_t* launches) {
+  if (!h || !ms || !flops || !bytes || !launches) return fail("bvg_profile_read: null argument");
+  for (int c = 0; c < PROF_NCLS; ++c) { ms[c] = flops[c] = bytes[c] = 0.0; launches[c] = 0; }
+  for (const ProfRec& r : h->prof) {
+    CK(cudaEventSynchronize(r.e1));
+    float t = 0.f;
+    CK(cudaEventElapsedTime(&t, r.e0, r.e1));
+    ms[r.cls] += t; flops[r.cls] += r.flops; bytes[r.cls] += r.bytes; launches[r.cls] += 1;
+  }
+  h->prof.clear();
+  h->ev_used = 0;
+  return 0;
+}
+
+int bvg_workspace_reset(bvg_handle* h) {
+  if (!h) return fail("bvg_workspace_reset: null handle");
+  h->ws_owner.clear();
+  return 0;
+}
+
+int bvg_forward_host(bvg_handle* h, bvg_plan* p, const void* latent_host, int32_t latent_dtype, void* latent_dev,
+                     const float* spk_emb, int32_t spk_batch, float* wav_host, float* wav_dev, void* workspace,
+                     size_t workspace_bytes, void* stream) {
+  if (!h || !p || !latent_host || !latent_dev || !wav_host || !wav_dev) return fail("bvg_forward_host: null argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t esz = latent_dtype == BVG_F32 ? 4 : 2;
+  const size_t in_bytes = (size_t)p->B * p->max_frames * h->cfg.gpt_dim * esz;
+  const size_t out_bytes = (size_t)p->B * p->max_frames * h->hop * sizeof(float);
+  CK(cudaMemcpyAsync(latent_dev, latent_host, in_bytes, cudaMemcpyHostToDevice, s));
+  if (bvg_forward(h, p, latent_dev, latent_dtype, spk_emb, spk_batch, wav_dev, workspace, workspace_bytes, stream))
+    return 1;
+  CK(cudaMemcpyAsync(wav_host, wav_dev, out_bytes, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// per-op entry points
+// ------------------------------------------------------------------------------------------
+int bvg_activation1d(const void* x, void* y, const float* log_alpha, const float* log_beta, int32_t B, int32_t C,
+                     int32_t T, int32_t dtype, void* stream) {
+  if (bvg_device_check()) return 1;
+  if (!x || !y || !log_alpha || !log_beta) return fail("bvg_activation1d: null argument");
+  if (dtype < 0 || dtype > 2) return fail("bvg_activation1d: dtype must be F32, BF16 or F16");
+  if (B <= 0 || C <= 0 || T <= 0) return 0;   // the reference returns early for seq_len == 0 (.cu:194-197)
+  cudaStream_t s = (cudaStream_t)stream;
+  float* prm = nullptr;
+  CK(cudaMallocAsync((void**)&prm, 2 * (size_t)C * sizeof(float), s));
+  cudaError_t e = launch_snake_params(log_alpha, log_beta, prm, prm + C, C, s);
+  if (e == cudaSuccess) e = launch_act_nct(x, y, prm, prm + C, B, C, T, dtype, s);
+  cudaFreeAsync(prm, s);
+  CK(e);
+  return 0;
+}
+
+namespace {
+struct OpTemps {
+  std::vector<void*> ptrs;
+  ~OpTemps() { for (void* p : ptrs) cudaFree(p); }
+  int alloc(void** p, size_t bytes) {
+    CK(cudaMalloc(p, bytes ? bytes : 4));
+    ptrs.push_back(*p);
+    return 0;
+  }
+};
+
+int conv_op(bool transposed, const float* x, const float* w, const float* bias, const float* residual, float* y,
+            int B, int Cin, int Cout, int T, int k, int d, int u, int mode, cudaStream_t s) {
+  if (bvg_device_check()) return 1;
+  if (!x || !w || !y) return fail("conv op: null argument");
+  if (Cin % 8 || Cout % 8) return fail("conv op: Cin and Cout must be multiples of 8");
+  if (k < 1 || (!transposed && (k > BVG_MAX_TAPS || !(k & 1))) || (transposed && (k % u || (k - u) % 2)))
+    return fail("conv op: unsupported kernel size");
+  ConvLayer L;
+  L.transposed = transposed; L.Cin = Cin; L.Cout = Cout; L.k = k; L.d = d; L.u = u; L.setup();
+  if (!transposed && (k - 1) / 2 * d > BVG_GUARD - 6) return fail("conv op: halo exceeds guard rows");
+  const int dt = mode == BVG_MODE_FP32 ? 0 : 1;
+  const size_t es = dt == 0 ? 4 : 2;
+  const int Tout = T * u;
+  OpTemps tmp;
+  std::vector<SegDesc> seg(2 * (size_t)B);
+  int Rin = BVG_GUARD, Rout = BVG_GUARD;
+  for (int b = 0; b < B; ++b) {
+    seg[b] = SegDesc{Rin, T}; Rin += T + BVG_GUARD;
+    seg[B + b] = SegDesc{Rout, Tout}; Rout += Tout + BVG_GUARD;
+  }
+  Rin += BVG_TAIL_SLACK; Rout += BVG_TAIL_SLACK;
+  SegDesc* seg_dev; void *xc, *yc, *rc = nullptr; float* wt; void* wu = nullptr;
+  if (tmp.alloc((void**)&seg_dev, seg.size() * sizeof(SegDesc))) return 1;
+  CK(cudaMemcpyAsync(seg_dev, seg.data(), seg.size() * sizeof(SegDesc), cudaMemcpyHostToDevice, s));
+  if (tmp.alloc(&xc, (size_t)Cin * Rin * es) || tmp.alloc(&yc, (size_t)Cout * Rout * es)) return 1;
+  CK(cudaMemsetAsync(xc, 0, (size_t)Cin * Rin * es, s));
+  CK(cudaMemsetAsync(yc, 0, (size_t)Cout * Rout * es, s));
+  CK(launch_nct_to_c8(x, xc, dt, seg_dev, B, Cin, T, Rin, s));
+  if (residual) {
+    if (tmp.alloc(&rc, (size_t)Cout * Rout * es)) return 1;
+    CK(cudaMemsetAsync(rc, 0, (size_t)Cout * Rout * es, s));
+    CK(launch_nct_to_c8(residual, rc, dt, seg_dev + B, B, Cout, Tout, Rout, s));
+  }
+  if (tmp.alloc((void**)&wt, (size_t)Cin * Cout * k * sizeof(float))) return 1;
+  if (transposed) CK(launch_repack_convt(w, wt, Cin, Cout, k, u, s));
+  else CK(launch_repack_conv(w, wt, Cout, Cin, k, s));
+  ConvArgs a{};
+  a.x = xc; a.y = yc; a.res = rc; a.w = wt; a.bias = bias; a.bias_bstride = 0;
+  a.seg_in = seg_dev; a.seg_out = seg_dev + B; a.Rx = Rin; a.Ry = Rout;
+  a.Cin = Cin; a.Cout = Cout; a.ntaps = L.ntaps;
+  for (int j = 0; j < L.ntaps; ++j) a.tap_off[j] = L.tap_off[j];
+  a.u = L.u; a.p = L.p; a.q_extra = L.q_extra; a.B = B; a.max_q = T + L.q_extra;
+  a.out_scale = 1.f; a.accumulate = 0;
+  if (mode == BVG_MODE_BF16) {
+    size_t bytes = umma_weight_image_bytes(L.ntaps, Cin, L.N);
+    if (!bytes || !conv_umma_supported(a)) return fail("conv op: shape not supported by the tcgen05 kernel");
+    if (tmp.alloc(&wu, bytes)) return 1;
+    CK(launch_repack_umma(wt, wu, L.ntaps, Cin, L.N, s));
+    a.w = wu;
+    CK(launch_conv_umma(a, s));
+  } else {
+    CK(launch_conv_simt(a, dt, s));
+  }
+  CK(launch_c8_to_nct(yc, dt, y, seg_dev + B, B, Cout, Tout, Rout, s));
+  CK(cudaStreamSynchronize(s));
+  return 0;
+}
+}  // namespace
+
+int bvg_conv1d(const float* x, const float* w, const float* bias, const float* residual, float* y, int32_t B,
+               int32_t Cin, int32_t Cout, int32_t T, int32_t k, int32_t dilation, int32_t mode, void* stream) {
+  return conv_op(false, x, w, bias, residual, y, B, Cin, Cout, T, k, dilation, 1, mode, (cudaStream_t)stream);
+}
+
+int bvg_conv_transpose1d(const float* x, const float* w, const float* bias, float* y, int32_t B, int32_t Cin,
+                         int32_t Cout, int32_t T, int32_t k, int32_t u, int32_t mode, void* stream) {
+  return conv_op(true, x, w, bias, nullptr, y, B, Cin, Cout, T, k, 1, u, mode, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,113 @@
+// Internal declarations shared by the b200vgan kernels (sm_100a only).
+//
+// Data layout in HBM ("packed c8"): an activation tensor with C channels (C % 8 == 0) over a
+// batch of variable-length segments is stored as  [C/8][R][8]  where R is ONE packed time axis:
+//
+//     | G zero rows | segment 0 (len0 rows) | G zero rows | segment 1 | ... | G + slack zero rows |
+//
+// element (b, t, c)  ->  ((c/8) * R + off[b] + t) * 8 + (c % 8).
+// The guard rows are zeroed once (workspace init) and never written afterwards, so the "same"
+// zero padding of every convolution, and the halo of every tile, is a plain in-bounds read.
+// An 8-channel group of one time step is one 16-byte (bf16) / 32-byte (fp32) vector: that is
+// the K-chunk ("core matrix row") of the tcgen05 no-swizzle K-major operand layout, so an
+// activation tile [rows][64 ch] maps to UMMA shared memory with a row stride of 16 B and any
+// dilated tap is a descriptor start-address shift (see bvg_conv_umma.cu).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define BVG_GUARD 32          // zero rows between segments (>= max conv halo 25 + act halo 5)
+#define BVG_TAIL_SLACK 320    // extra zero rows after the last segment (tile overrun of loads)
+#define BVG_MAX_TAPS 11
+
+struct SegDesc {   // one per (stage, segment)
+  int off;         // first row of the segment on the packed time axis
+  int len;         // valid rows
+};
+
+struct ConvArgs {
+  const void* x;        // [Cin/8][Rx][8]
+  void* y;              // [Cout/8][Ry][8]
+  const void* res;      // residual, geometry of y, or nullptr
+  const void* w;        // kernel-specific weight image
+  const float* bias;    // bias[b * bias_bstride + co]
+  const SegDesc* seg_in;
+  const SegDesc* seg_out;
+  int bias_bstride;
+  int Rx, Ry;
+  int Cin, Cout;        // Cout = channels of y; GEMM N = u * Cout
+  int ntaps;
+  int tap_off[BVG_MAX_TAPS];  // input row = q + tap_off[j]
+  int u, p;             // output row = q*u + phase - p  (u = 1, p = 0: plain conv)
+  int q_extra;          // tiles cover q in [0, len_in + q_extra)
+  int B;
+  int max_q;            // max over segments of (len_in + q_extra)
+  float out_scale;      // y = (acc + bias + res) * out_scale (+ y_old if accumulate)
+  int accumulate;
+};
+
+struct ActArgs {
+  const void* x;
+  void* y;
+  const float* alpha;     // exp(log_alpha)  [C]
+  const float* inv_beta;  // 1 / (exp(log_beta) + 1e-9)  [C]
+  const SegDesc* seg;
+  int R, C, B, max_len;
+};
+
+// -------------------------------------------------------------------------------------------
+template <typename T> struct Vec8;   // 8 consecutive channels of one time step
+template <> struct Vec8<float> {
+  float v[8];
+  __device__ __forceinline__ void load(const float* p) {
+    float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+  __device__ __forceinline__ void store(float* p) const {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  }
+};
+template <> struct Vec8<__nv_bfloat16> {
+  float v[8];
+  __device__ __forceinline__ void load(const __nv_bfloat16* p) {
+    uint4 r = *reinterpret_cast<const uint4*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+  }
+  __device__ __forceinline__ void store(__nv_bfloat16* p) const {
+    uint4 r;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    *reinterpret_cast<uint4*>(p) = r;
+  }
+};
+
+__device__ __forceinline__ float to_f32(float x) { return x; }
+__device__ __forceinline__ float to_f32(__nv_bfloat16 x) { return __bfloat162float(x); }
+__device__ __forceinline__ float to_f32(__half x) { return __half2float(x); }
+template <typename T> __device__ __forceinline__ T from_f32(float x);
+template <> __device__ __forceinline__ float from_f32<float>(float x) { return x; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float x) { return __float2bfloat16_rn(x); }
+template <> __device__ __forceinline__ __half from_f32<__half>(float x) { return __float2half_rn(x); }
+
+// kaiser_sinc_filter1d(0.25, 0.3, 12) -- reference alias_free_torch/filter.py:29-58; the taps are
+// symmetric, sum to 1 and are shared by UpSample1d and DownSample1d.
+#define BVG_F0 0.00202896469f
+#define BVG_F1 0.00938946567f
+#define BVG_F2 (-0.0255434588f)
+#define BVG_F3 (-0.0576573834f)
+#define BVG_F4 0.128572583f
+#define BVG_F5 0.443209797f
+
+// host-side launchers (each returns cudaGetLastError())
+cudaError_t launch_act_c8(const ActArgs& a, int dtype, bool precise, cudaStream_t s);
+cudaError_t launch_act_nct(const void* x, void* y, const float* alpha, const float* inv_beta, int B, int C,
+                           int T, int dtype, cudaStream_t s);
+cudaError_t launch_conv_simt(const ConvArgs& a, int dtype, cudaStream_t s);
+cudaError_t launch_conv_umma(const ConvArgs& a, cudaStream_t s);
+bool conv_umma_supported(const ConvArgs& a);

@@ -1,0 +1,222 @@
+// Small kernels around the convolution / activation hot ops: layout packing, weight repacking,
+// the speaker-conditioning projection folded into per-segment biases, and conv_post + tanh.
+#include "bvg_common.cuh"
+#include "bvg_misc.cuh"
+
+namespace {
+
+// latent [B, Tmax, C] row-major (any float type)  ->  packed c8 [C/8][R][8]
+template <typename TI, typename TO>
+__global__ void pack_latent_kernel(const TI* __restrict__ x, TO* __restrict__ y, const SegDesc* __restrict__ seg,
+                                   int B, int Tmax, int C, int R) {
+  const int nch = C >> 3;
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t total = (size_t)B * Tmax * nch;
+  if (idx >= total) return;
+  int chunk = idx % nch;
+  size_t bt = idx / nch;
+  int t = bt % Tmax, b = bt / Tmax;
+  SegDesc sd = seg[b];
+  if (t >= sd.len) return;
+  const TI* p = x + ((size_t)b * Tmax + t) * C + chunk * 8;
+  Vec8<TO> v;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) v.v[c] = to_f32(p[c]);
+  v.store(y + ((size_t)chunk * R + sd.off + t) * 8);
+}
+
+// fp32 [B, C, T]  <->  packed c8 (test entry points only)
+template <typename TO>
+__global__ void nct_to_c8_kernel(const float* __restrict__ x, TO* __restrict__ y, const SegDesc* __restrict__ seg,
+                                 int B, int C, int T, int R) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t total = (size_t)B * C * T;
+  if (idx >= total) return;
+  int t = idx % T;
+  size_t bc = idx / T;
+  int c = bc % C, b = bc / C;
+  y[((size_t)(c >> 3) * R + seg[b].off + t) * 8 + (c & 7)] = from_f32<TO>(x[idx]);
+}
+template <typename TI>
+__global__ void c8_to_nct_kernel(const TI* __restrict__ x, float* __restrict__ y, const SegDesc* __restrict__ seg,
+                                 int B, int C, int T, int R) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t total = (size_t)B * C * T;
+  if (idx >= total) return;
+  int t = idx % T;
+  size_t bc = idx / T;
+  int c = bc % C, b = bc / C;
+  y[idx] = to_f32(x[((size_t)(c >> 3) * R + seg[b].off + t) * 8 + (c & 7)]);
+}
+
+// out[b][co] = bias[co] + cond_b[co] + sum_k cond_w[co][k] spk[b % spkB][k]     (one warp per output)
+// reference: models.py:192-197 (1x1 convs on the [B',512,1] embedding), :226, :233-234 (broadcast add)
+__global__ void cond_bias_kernel(const float* __restrict__ bias, const float* __restrict__ cw,
+                                 const float* __restrict__ cb, const float* __restrict__ spk, float* __restrict__ out,
+                                 int C, int D, int B, int spkB, int out_bstride) {
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= B * C) return;
+  int b = warp / C, co = warp - b * C;
+  float acc = 0.f;
+  if (cw) {
+    const float* w = cw + (size_t)co * D;
+    const float* s = spk + (size_t)(spkB == 1 ? 0 : b) * D;
+    for (int k = lane; k < D; k += 32) acc = fmaf(w[k], s[k], acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  }
+  if (lane == 0) out[(size_t)b * out_bstride + co] = acc + bias[co] + (cb ? cb[co] : 0.f);
+}
+
+// conv_post (C -> 1, k = 7, pad 3) + tanh  (models.py:184, :247-248), C <= 64.  wav [B][Lmax] fp32.
+template <typename T>
+__global__ void conv_post_tanh_kernel(const T* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                                      float* __restrict__ wav, const SegDesc* __restrict__ seg, int C, int R,
+                                      int Lmax) {
+  __shared__ float ws[7][64];
+  for (int i = threadIdx.x; i < 7 * C; i += blockDim.x) {
+    int j = i / C, c = i - j * C;
+    ws[j][c] = w[c * 7 + j];   // w [1][C][7]
+  }
+  __syncthreads();
+  const int b = blockIdx.y;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= Lmax) return;
+  SegDesc sd = seg[b];
+  float out = 0.f;
+  if (t < sd.len) {
+    float acc = bias[0];
+    const int nch = C >> 3;
+    for (int ch = 0; ch < nch; ++ch) {
+      const T* p = x + ((size_t)ch * R + sd.off + t - 3) * 8;
+#pragma unroll
+      for (int j = 0; j < 7; ++j) {
+        Vec8<T> v;
+        v.load(p + j * 8);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc = fmaf(v.v[c], ws[j][ch * 8 + c], acc);
+      }
+    }
+    out = tanhf(acc);
+  }
+  wav[(size_t)b * Lmax + t] = out;
+}
+
+// Conv1d weight [Cout][Cin][k] -> [k][Cin][Cout]
+__global__ void repack_conv_kernel(const float* __restrict__ w, float* __restrict__ wp, int Cout, int Cin, int k) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t total = (size_t)Cout * Cin * k;
+  if (idx >= total) return;
+  int co = idx % Cout;
+  size_t r = idx / Cout;
+  int ci = r % Cin, j = r / Cin;
+  wp[idx] = w[((size_t)co * Cin + ci) * k + j];
+}
+// ConvTranspose1d weight [Cin][Cout][k] -> [k/u][Cin][u*Cout],  wp[m][ci][phi*Cout+co] = w[ci][co][phi+m*u]
+__global__ void repack_convt_kernel(const float* __restrict__ w, float* __restrict__ wp, int Cin, int Cout, int k,
+                                    int u) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t total = (size_t)Cin * Cout * k;
+  if (idx >= total) return;
+  int N = u * Cout;
+  int n = idx % N;
+  size_t r = idx / N;
+  int ci = r % Cin, m = r / Cin;
+  int phi = n / Cout, co = n - phi * Cout;
+  wp[idx] = w[((size_t)ci * Cout + co) * k + phi + m * u];
+}
+
+__global__ void snake_params_kernel(const float* __restrict__ la, const float* __restrict__ lb,
+                                    float* __restrict__ alpha, float* __restrict__ inv_beta, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  alpha[i] = expf(la[i]);                       // activations.py:115-118 (alpha_logscale)
+  inv_beta[i] = 1.0f / (expf(lb[i]) + 1e-9f);   // activations.py:120 (no_div_by_zero)
+}
+
+// Zero every row of a packed c8 buffer that belongs to no segment (the guard gaps and the tail
+// slack).  gap g lies between segment g-1 and segment g; block = (gap, chunk).
+__global__ void zero_guards_kernel(uint4* __restrict__ buf, const SegDesc* __restrict__ seg, int B, int R,
+                                   int vec_per_row) {
+  const int g = blockIdx.x, chunk = blockIdx.y;
+  const int lo = g == 0 ? 0 : seg[g - 1].off + seg[g - 1].len;
+  const int hi = g == B ? R : seg[g].off;
+  uint4* p = buf + ((size_t)chunk * R + lo) * vec_per_row;
+  const int n = (hi - lo) * vec_per_row;
+  const uint4 z = make_uint4(0, 0, 0, 0);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) p[i] = z;
+}
+
+inline int nblk(size_t n, int t) { return (int)((n + t - 1) / t); }
+
+}  // namespace
+
+cudaError_t launch_pack_latent(const void* x, int in_dtype, void* y, int out_dtype, const SegDesc* seg, int B,
+                               int Tmax, int C, int R, cudaStream_t s) {
+  size_t total = (size_t)B * Tmax * (C >> 3);
+  if (!total) return cudaSuccess;
+  dim3 g(nblk(total, 256)), blk(256);
+#define PL(TI, TO) pack_latent_kernel<TI, TO><<<g, blk, 0, s>>>((const TI*)x, (TO*)y, seg, B, Tmax, C, R)
+  if (out_dtype == 0) {
+    if (in_dtype == 0) PL(float, float); else if (in_dtype == 1) PL(__nv_bfloat16, float); else PL(__half, float);
+  } else {
+    if (in_dtype == 0) PL(float, __nv_bfloat16); else if (in_dtype == 1) PL(__nv_bfloat16, __nv_bfloat16); else PL(__half, __nv_bfloat16);
+  }
+#undef PL
+  return cudaGetLastError();
+}
+
+cudaError_t launch_nct_to_c8(const float* x, void* y, int out_dtype, const SegDesc* seg, int B, int C, int T, int R,
+                             cudaStream_t s) {
+  size_t total = (size_t)B * C * T;
+  if (!total) return cudaSuccess;
+  if (out_dtype == 0) nct_to_c8_kernel<float><<<nblk(total, 256), 256, 0, s>>>(x, (float*)y, seg, B, C, T, R);
+  else nct_to_c8_kernel<__nv_bfloat16><<<nblk(total, 256), 256, 0, s>>>(x, (__nv_bfloat16*)y, seg, B, C, T, R);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_c8_to_nct(const void* x, int in_dtype, float* y, const SegDesc* seg, int B, int C, int T, int R,
+                             cudaStream_t s) {
+  size_t total = (size_t)B * C * T;
+  if (!total) return cudaSuccess;
+  if (in_dtype == 0) c8_to_nct_kernel<float><<<nblk(total, 256), 256, 0, s>>>((const float*)x, y, seg, B, C, T, R);
+  else c8_to_nct_kernel<__nv_bfloat16><<<nblk(total, 256), 256, 0, s>>>((const __nv_bfloat16*)x, y, seg, B, C, T, R);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_cond_bias(const float* bias, const float* cw, const float* cb, const float* spk, float* out, int C,
+                             int D, int B, int spkB, int out_bstride, cudaStream_t s) {
+  size_t threads = (size_t)B * C * 32;
+  cond_bias_kernel<<<nblk(threads, 256), 256, 0, s>>>(bias, cw, cb, spk, out, C, D, B, spkB, out_bstride);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_conv_post_tanh(const void* x, int dtype, const float* w, const float* bias, float* wav,
+                                  const SegDesc* seg, int B, int C, int R, int Lmax, cudaStream_t s) {
+  if (B <= 0 || Lmax <= 0) return cudaSuccess;
+  dim3 g(nblk(Lmax, 256), B), blk(256);
+  if (dtype == 0) conv_post_tanh_kernel<float><<<g, blk, 0, s>>>((const float*)x, w, bias, wav, seg, C, R, Lmax);
+  else conv_post_tanh_kernel<__nv_bfloat16><<<g, blk, 0, s>>>((const __nv_bfloat16*)x, w, bias, wav, seg, C, R, Lmax);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_repack_conv(const float* w, float* wp, int Cout, int Cin, int k, cudaStream_t s) {
+  size_t total = (size_t)Cout * Cin * k;
+  repack_conv_kernel<<<nblk(total, 256), 256, 0, s>>>(w, wp, Cout, Cin, k);
+  return cudaGetLastError();
+}
+cudaError_t launch_repack_convt(const float* w, float* wp, int Cin, int Cout, int k, int u, cudaStream_t s) {
+  size_t total = (size_t)Cin * Cout * k;
+  repack_convt_kernel<<<nblk(total, 256), 256, 0, s>>>(w, wp, Cin, Cout, k, u);
+  return cudaGetLastError();
+}
+cudaError_t launch_snake_params(const float* la, const float* lb, float* alpha, float* inv_beta, int n,
+                                cudaStream_t s) {
+  snake_params_kernel<<<nblk(n, 256), 256, 0, s>>>(la, lb, alpha, inv_beta, n);
+  return cudaGetLastError();
+}
+cudaError_t launch_zero_guards(void* buf, int esize, const SegDesc* seg, int B, int C, int R, cudaStream_t s) {
+  dim3 g(B + 1, C >> 3);
+  zero_guards_kernel<<<g, 128, 0, s>>>((uint4*)buf, seg, B, R, esize == 4 ? 2 : 1);
+  return cudaGetLastError();
+}

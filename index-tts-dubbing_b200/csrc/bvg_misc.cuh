@@ -1,0 +1,21 @@
+#pragma once
+#include "bvg_common.cuh"
+
+cudaError_t launch_pack_latent(const void* x, int in_dtype, void* y, int out_dtype, const SegDesc* seg, int B,
+                               int Tmax, int C, int R, cudaStream_t s);
+cudaError_t launch_nct_to_c8(const float* x, void* y, int out_dtype, const SegDesc* seg, int B, int C, int T, int R,
+                             cudaStream_t s);
+cudaError_t launch_c8_to_nct(const void* x, int in_dtype, float* y, const SegDesc* seg, int B, int C, int T, int R,
+                             cudaStream_t s);
+cudaError_t launch_cond_bias(const float* bias, const float* cw, const float* cb, const float* spk, float* out, int C,
+                             int D, int B, int spkB, int out_bstride, cudaStream_t s);
+cudaError_t launch_conv_post_tanh(const void* x, int dtype, const float* w, const float* bias, float* wav,
+                                  const SegDesc* seg, int B, int C, int R, int Lmax, cudaStream_t s);
+cudaError_t launch_repack_conv(const float* w, float* wp, int Cout, int Cin, int k, cudaStream_t s);
+cudaError_t launch_repack_convt(const float* w, float* wp, int Cin, int Cout, int k, int u, cudaStream_t s);
+cudaError_t launch_snake_params(const float* la, const float* lb, float* alpha, float* inv_beta, int n,
+                                cudaStream_t s);
+// bf16 UMMA weight images (bvg_conv_umma.cu)
+size_t umma_weight_image_bytes(int ntaps, int Cin, int N);
+cudaError_t launch_repack_umma(const float* wp_tap_major, void* img, int ntaps, int Cin, int N, cudaStream_t s);
+cudaError_t launch_zero_guards(void* buf, int esize, const SegDesc* seg, int B, int C, int R, cudaStream_t s);

@@ -1,0 +1,132 @@
+"""-m gpu: per-op parity of the CUDA kernels against the oracle / golden fixtures, through the C ABI."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import bigvgan_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_gpu():
+    if not torch.cuda.is_available():
+        pytest.fail("GPU test selected but no CUDA device is visible (there is no CPU fallback)")
+
+
+@pytest.mark.parametrize("case", ["a", "b", "c", "d"])
+def test_activation1d_golden_fp32(golden_dir, case):
+    from tests import gpu_util as G
+    g = np.load(os.path.join(golden_dir, "activation1d.npz"))
+    y = G.activation1d(g[f"{case}_x"], g[f"{case}_alpha"], g[f"{case}_beta"])
+    np.testing.assert_allclose(y, g[f"{case}_y"], atol=1e-5)
+
+
+@pytest.mark.parametrize("shape", [(2, 40, 1000), (1, 3, 5), (3, 8, 257), (1, 24, 4096 + 17)])
+def test_activation1d_oracle_fp32(shape):
+    from tests import gpu_util as G
+    rng = np.random.default_rng(hash(shape) % 1000)
+    x = (1.5 * rng.standard_normal(shape)).astype(np.float32)
+    la = (0.5 * rng.standard_normal(shape[1])).astype(np.float32)
+    lb = (0.5 * rng.standard_normal(shape[1])).astype(np.float32)
+    ref = O.activation1d(x.astype(np.float64), la.astype(np.float64), lb.astype(np.float64))
+    np.testing.assert_allclose(G.activation1d(x, la, lb), ref, atol=2e-5)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.bfloat16, 4e-2), (torch.float16, 6e-3)])
+def test_activation1d_half_types(dtype, tol):
+    from tests import gpu_util as G
+    rng = np.random.default_rng(5)
+    x = (1.5 * rng.standard_normal((2, 16, 700))).astype(np.float32)
+    la = (0.5 * rng.standard_normal(16)).astype(np.float32)
+    lb = (0.5 * rng.standard_normal(16)).astype(np.float32)
+    xr = torch.as_tensor(x).to(dtype).float().numpy().astype(np.float64)
+    ref = O.activation1d(xr, la.astype(np.float64), lb.astype(np.float64))
+    y = G.activation1d(x, la, lb, dtype)
+    assert np.abs(y - ref).max() <= tol * max(1.0, np.abs(ref).max())
+
+
+def test_activation1d_empty_is_noop():
+    from tests import gpu_util as G
+    from b200vgan import lib
+    z = torch.zeros(1, device="cuda")
+    lib.check(G.L_().bvg_activation1d(z.data_ptr(), z.data_ptr(), z.data_ptr(), z.data_ptr(), 1, 8, 0, 0, None))
+
+
+CONV_CASES = [  # (B, Cin, Cout, T, k, d)
+    (1, 16, 24, 50, 3, 1), (2, 24, 24, 300, 7, 3), (1, 64, 48, 257, 11, 5), (2, 8, 8, 1, 3, 1),
+    (1, 96, 96, 200, 7, 1), (1, 1024, 64, 40, 7, 1),
+]
+
+
+def _conv_inputs(B, Cin, Cout, T, k, seed):
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((B, Cin, T)).astype(np.float32)
+    w = (rng.standard_normal((Cout, Cin, k)) / np.sqrt(Cin * k)).astype(np.float32)
+    b = (0.1 * rng.standard_normal(Cout)).astype(np.float32)
+    r = rng.standard_normal((B, Cout, T)).astype(np.float32)
+    return x, w, b, r
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv1d_cuda_core_fp32(case):
+    from tests import gpu_util as G
+    B, Cin, Cout, T, k, d = case
+    x, w, b, r = _conv_inputs(B, Cin, Cout, T, k, 1)
+    ref = O.conv1d(x.astype(np.float64), w.astype(np.float64), b.astype(np.float64), dilation=d,
+                   padding=O.get_padding(k, d)) + r
+    y = G.conv1d(x, w, b, r, k, d, 0)
+    np.testing.assert_allclose(y, ref, atol=2e-5, rtol=1e-5)
+    y = G.conv1d(x, w, None, None, k, d, 0)
+    np.testing.assert_allclose(y, ref - r - b[None, :, None], atol=2e-5, rtol=1e-5)
+
+
+CONVT_CASES = [(1, 32, 16, 37, 8, 4), (2, 16, 8, 5, 4, 4), (1, 48, 24, 130, 4, 2), (1, 64, 32, 1, 8, 4)]
+
+
+@pytest.mark.parametrize("case", CONVT_CASES)
+def test_conv_transpose1d_cuda_core_fp32(case):
+    from tests import gpu_util as G
+    B, Cin, Cout, T, k, u = case
+    rng = np.random.default_rng(2)
+    x = rng.standard_normal((B, Cin, T)).astype(np.float32)
+    w = (rng.standard_normal((Cin, Cout, k)) / np.sqrt(Cin * k / u)).astype(np.float32)
+    b = (0.1 * rng.standard_normal(Cout)).astype(np.float32)
+    ref = O.conv_transpose1d(x.astype(np.float64), w.astype(np.float64), b.astype(np.float64), u, (k - u) // 2)
+    np.testing.assert_allclose(G.conv_transpose1d(x, w, b, k, u, 0), ref, atol=2e-5, rtol=1e-5)
+
+
+UMMA_CONV_CASES = [  # (B, Cin, Cout, T, k, d)
+    (1, 64, 64, 128, 3, 1), (1, 64, 64, 300, 3, 1), (2, 192, 192, 260, 7, 3), (1, 96, 96, 515, 11, 5),
+    (1, 48, 48, 700, 7, 5), (1, 24, 24, 1000, 11, 1), (1, 128, 128, 130, 3, 3), (1, 256, 768, 300, 3, 5),
+    (2, 384, 384, 200, 11, 5), (1, 1024, 1536, 100, 7, 1), (3, 768, 768, 77, 7, 1),
+]
+
+
+@pytest.mark.parametrize("case", UMMA_CONV_CASES)
+def test_conv1d_tcgen05_bf16(case):
+    from tests import gpu_util as G
+    B, Cin, Cout, T, k, d = case
+    x, w, b, r = _conv_inputs(B, Cin, Cout, T, k, 3)
+    ref = O.conv1d(G.bf16_round(x), G.bf16_round(w), b.astype(np.float64), dilation=d,
+                   padding=O.get_padding(k, d)) + G.bf16_round(r)
+    y = G.conv1d(x, w, b, r, k, d, 1)
+    scale = np.abs(ref).max()
+    assert np.abs(y - ref).max() <= 8e-3 * scale, (np.abs(y - ref).max(), scale)
+
+
+@pytest.mark.parametrize("case", [(1, 64, 32, 100, 8, 4), (2, 192, 96, 50, 4, 4), (1, 48, 24, 300, 4, 2),
+                                  (1, 1536, 768, 40, 8, 4), (1, 96, 48, 129, 4, 2)])
+def test_conv_transpose1d_tcgen05_bf16(case):
+    from tests import gpu_util as G
+    B, Cin, Cout, T, k, u = case
+    rng = np.random.default_rng(4)
+    x = rng.standard_normal((B, Cin, T)).astype(np.float32)
+    w = (rng.standard_normal((Cin, Cout, k)) / np.sqrt(Cin * k / u)).astype(np.float32)
+    b = (0.1 * rng.standard_normal(Cout)).astype(np.float32)
+    ref = O.conv_transpose1d(G.bf16_round(x), G.bf16_round(w), b.astype(np.float64), u, (k - u) // 2)
+    y = G.conv_transpose1d(x, w, b, k, u, 1)
+    scale = np.abs(ref).max()
+    assert np.abs(y - ref).max() <= 8e-3 * scale, (np.abs(y - ref).max(), scale)
