@@ -201,7 +201,8 @@ class BigVGAN(nn.Module):
         if cache_key is not None and cache_key in self._spk_cache:
             return self._spk_cache[cache_key]
         dev = self.conv_pre.bias.device
-        emb = self.speaker_encoder(mel_ref.to(dev), None if lens is None else lens.to(dev)).float().contiguous()
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):   # keep the embedding fp32-exact
+            emb = self.speaker_encoder(mel_ref.to(dev), None if lens is None else lens.to(dev)).float().contiguous()
         if cache_key is not None:
             self._spk_cache[cache_key] = emb
         return emb
