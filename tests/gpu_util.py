@@ -33,7 +33,8 @@ def activation1d(x, la, lb, dtype=torch.float32):
     y = torch.empty_like(xt)
     B, Cc, T = xt.shape
     code = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}[dtype]
-    lib.check(L_().bvg_activation1d(ptr(xt), ptr(y), ptr(dev(la)), ptr(dev(lb)), B, Cc, T, code, stream()))
+    lat, lbt = dev(la), dev(lb)      # keep the parameter tensors alive across the call
+    lib.check(L_().bvg_activation1d(ptr(xt), ptr(y), ptr(lat), ptr(lbt), B, Cc, T, code, stream()))
     torch.cuda.synchronize()
     return y.float().cpu().numpy()
 
