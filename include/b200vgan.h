@@ -145,6 +145,12 @@ int bvg_forward_host(bvg_handle* h, bvg_plan* plan, const void* latent_host, int
 int bvg_activation1d(const void* x, void* y, const float* log_alpha, const float* log_beta,
                      int32_t B, int32_t C, int32_t T, int32_t dtype, void* stream);
 
+/* The same function through the kernel bvg_forward uses (packed c8 layout, per-segment lengths):
+ * x,y [B,C,T] fp32 are packed / unpacked around it; C multiple of 8; mode as in bvg_forward
+ * (BVG_MODE_BF16 stores the packed tensors in bf16).  Test / tooling entry, allocates temporaries. */
+int bvg_activation1d_packed(const float* x, float* y, const float* log_alpha, const float* log_beta,
+                            int32_t B, int32_t C, int32_t T, int32_t mode, void* stream);
+
 /* Dense Conv1d, "same" zero padding d*(k-1)/2, stride 1 (torch.nn.Conv1d as used at
  * models.py:26-41,149).  x [B,Cin,T] fp32, w [Cout,Cin,k] fp32, bias [Cout] or NULL,
  * residual [B,Cout,T] or NULL, y [B,Cout,T] fp32.  Cin, Cout multiples of 8.

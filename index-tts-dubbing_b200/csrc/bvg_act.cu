@@ -14,6 +14,8 @@
 // One CTA = one 8-channel group x TR consecutive time steps of one segment.  The raw tile
 // (+-6 halo rows) is staged in shared memory channel-major so the FIRs read conflict-free
 // along time; each warp owns one channel.  HBM traffic is the algorithmic 2 * elements.
+#include <cstdlib>
+
 #include "bvg_common.cuh"
 
 namespace {
@@ -132,6 +134,11 @@ act1d_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __restrict
 
 cudaError_t launch_act_c8(const ActArgs& a, int dtype, bool precise, cudaStream_t s) {
   if (a.B <= 0 || a.max_len <= 0) return cudaSuccess;
+  // v2 (warp-autonomous, register-streamed) is the default; BVG_ACT_V1=1 selects the first version
+  // and BVG_ACT_RT=16|32 the rows per thread (A/B knobs used while tuning on the GPU box).
+  static const int use_v1 = [] { const char* e = getenv("BVG_ACT_V1"); return (e && e[0] == '1') ? 1 : 0; }();
+  static const int rt = [] { const char* e = getenv("BVG_ACT_RT"); int v = e ? atoi(e) : 32; return (v == 16 || v == 24) ? v : 32; }();
+  if (!use_v1) return launch_act_c8_v2(a, dtype, precise, rt, s);
   dim3 grid((a.max_len + TR - 1) / TR, a.C / 8, a.B), block(NTHREADS);
   if (dtype == 0) {
     if (precise)

@@ -141,6 +141,8 @@ struct bvg_plan {
   std::vector<int> R, maxlen, C;
   std::vector<long long> sumlen;   // valid rows over all segments, per geometry
   SegDesc* seg_dev = nullptr;   // [(nups+1)][B]
+  int* prefix_dev = nullptr;    // m-tile prefix tables [g][msub-1][q_extra][B+1]
+  std::vector<int> total_mt;    // [g][msub-1][q_extra]
   size_t ws_bytes = 0;
   size_t off_lat = 0, off_pre = 0, off_bias = 0;
   std::vector<size_t> off_U, off_X, off_A, off_Y, off_XS;
@@ -186,6 +188,10 @@ ConvArgs make_conv_args(const ConvLayer& L, const bvg_plan* p, int gin, int gout
   a.u = L.u; a.p = L.p; a.q_extra = L.q_extra;
   a.B = p->B; a.max_q = p->maxlen[gin] + L.q_extra;
   a.out_scale = scale; a.accumulate = accumulate;
+  a.msub = conv_umma_default_msub(a);
+  const int ti = (gin * 2 + (a.msub - 1)) * 2 + (L.q_extra ? 1 : 0);
+  a.tile_prefix = p->prefix_dev + (size_t)ti * (p->B + 1);
+  a.total_mt = p->total_mt[ti];
   return a;
 }
 
@@ -433,6 +439,24 @@ int bvg_plan_create(bvg_handle* h, int32_t B, const int32_t* frames, int32_t mod
     delete p;
     return fail("bvg_plan_create: segment table upload failed");
   }
+  {
+    std::vector<int> pref((size_t)ng * 4 * (B + 1));
+    p->total_mt.assign((size_t)ng * 4, 0);
+    for (int g = 0; g < ng; ++g)
+      for (int ms = 1; ms <= 2; ++ms)
+        for (int qe = 0; qe < 2; ++qe) {
+          const int ti = (g * 2 + (ms - 1)) * 2 + qe;
+          int* pf = pref.data() + (size_t)ti * (B + 1);
+          pf[0] = 0;
+          for (int b = 0; b < B; ++b) pf[b + 1] = pf[b] + (seg[(size_t)g * B + b].len + qe + 128 * ms - 1) / (128 * ms);
+          p->total_mt[ti] = pf[B];
+        }
+    if (cudaMalloc(&p->prefix_dev, pref.size() * sizeof(int)) != cudaSuccess ||
+        cudaMemcpy(p->prefix_dev, pref.data(), pref.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) {
+      delete p;
+      return fail("bvg_plan_create: tile table upload failed");
+    }
+  }
   // workspace carve-up
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
@@ -459,6 +483,7 @@ int bvg_plan_create(bvg_handle* h, int32_t B, const int32_t* frames, int32_t mod
 void bvg_plan_destroy(bvg_plan* p) {
   if (!p) return;
   if (p->seg_dev) cudaFree(p->seg_dev);
+  if (p->prefix_dev) cudaFree(p->prefix_dev);
   delete p;
 }
 size_t bvg_plan_workspace_bytes(const bvg_plan* p) { return p ? p->ws_bytes : 0; }
@@ -556,10 +581,14 @@ int bvg_profile_enable(bvg_handle* h, int32_t on) {
 int bvg_profile_read(bvg_handle* h, double* ms, double* flops, double* bytes, int64_t* launches) {
   if (!h || !ms || !flops || !bytes || !launches) return fail("bvg_profile_read: null argument");
   for (int c = 0; c < PROF_NCLS; ++c) { ms[c] = flops[c] = bytes[c] = 0.0; launches[c] = 0; }
+  const char* dump = getenv("BVG_PROF_DUMP");   // optional per-launch dump: "cls ms flops bytes" per line
+  FILE* df = dump ? fopen(dump, "w") : nullptr;
+  struct Closer { FILE* f; ~Closer() { if (f) fclose(f); } } closer{df};
   for (const ProfRec& r : h->prof) {
     CK(cudaEventSynchronize(r.e1));
     float t = 0.f;
     CK(cudaEventElapsedTime(&t, r.e0, r.e1));
+    if (df) fprintf(df, "%d %.6f %.6e %.6e\n", r.cls, t, r.flops, r.bytes);
     ms[r.cls] += t; flops[r.cls] += r.flops; bytes[r.cls] += r.bytes; launches[r.cls] += 1;
   }
   h->prof.clear();
@@ -662,7 +691,16 @@ int conv_op(bool transposed, const float* x, const float* w, const float* bias, 
   for (int j = 0; j < L.ntaps; ++j) a.tap_off[j] = L.tap_off[j];
   a.u = L.u; a.p = L.p; a.q_extra = L.q_extra; a.B = B; a.max_q = T + L.q_extra;
   a.out_scale = 1.f; a.accumulate = 0;
+  a.tile_prefix = nullptr; a.total_mt = 0; a.msub = 1;
   if (mode == BVG_MODE_BF16) {
+    a.msub = conv_umma_default_msub(a);
+    std::vector<int> pf(B + 1, 0);
+    for (int b = 0; b < B; ++b) pf[b + 1] = pf[b] + (T + L.q_extra + 128 * a.msub - 1) / (128 * a.msub);
+    int* pf_dev;
+    if (tmp.alloc((void**)&pf_dev, pf.size() * sizeof(int))) return 1;
+    CK(cudaMemcpyAsync(pf_dev, pf.data(), pf.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+    CK(cudaStreamSynchronize(s));
+    a.tile_prefix = pf_dev; a.total_mt = pf[B];
     size_t bytes = umma_weight_image_bytes(L.ntaps, Cin, L.N);
     if (!bytes || !conv_umma_supported(a)) return fail("conv op: shape not supported by the tcgen05 kernel");
     if (tmp.alloc(&wu, bytes)) return 1;
@@ -677,6 +715,34 @@ int conv_op(bool transposed, const float* x, const float* w, const float* bias, 
   return 0;
 }
 }  // namespace
+
+int bvg_activation1d_packed(const float* x, float* y, const float* log_alpha, const float* log_beta, int32_t B,
+                            int32_t C, int32_t T, int32_t mode, void* stream) {
+  if (bvg_device_check()) return 1;
+  if (!x || !y || !log_alpha || !log_beta) return fail("bvg_activation1d_packed: null argument");
+  if (C % 8 || B < 1 || T < 1) return fail("bvg_activation1d_packed: C must be a multiple of 8, B,T >= 1");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int dt = mode == BVG_MODE_FP32 ? 0 : 1;
+  const size_t es = dt == 0 ? 4 : 2;
+  OpTemps tmp;
+  std::vector<SegDesc> seg(B);
+  int R = BVG_GUARD;
+  for (int b = 0; b < B; ++b) { seg[b] = SegDesc{R, T}; R += T + BVG_GUARD; }
+  R += BVG_TAIL_SLACK;
+  SegDesc* seg_dev; void *xc, *yc; float* prm;
+  if (tmp.alloc((void**)&seg_dev, seg.size() * sizeof(SegDesc)) || tmp.alloc(&xc, (size_t)C * R * es) ||
+      tmp.alloc(&yc, (size_t)C * R * es) || tmp.alloc((void**)&prm, 2 * (size_t)C * sizeof(float))) return 1;
+  CK(cudaMemcpyAsync(seg_dev, seg.data(), seg.size() * sizeof(SegDesc), cudaMemcpyHostToDevice, s));
+  CK(cudaMemsetAsync(xc, 0, (size_t)C * R * es, s));
+  CK(cudaMemsetAsync(yc, 0, (size_t)C * R * es, s));
+  CK(launch_nct_to_c8(x, xc, dt, seg_dev, B, C, T, R, s));
+  CK(launch_snake_params(log_alpha, log_beta, prm, prm + C, C, s));
+  ActArgs aa{xc, yc, prm, prm + C, seg_dev, R, C, B, T};
+  CK(launch_act_c8(aa, dt, mode == BVG_MODE_FP32, s));
+  CK(launch_c8_to_nct(yc, dt, y, seg_dev, B, C, T, R, s));
+  CK(cudaStreamSynchronize(s));
+  return 0;
+}
 
 int bvg_conv1d(const float* x, const float* w, const float* bias, const float* residual, float* y, int32_t B,
                int32_t Cin, int32_t Cout, int32_t T, int32_t k, int32_t dilation, int32_t mode, void* stream) {

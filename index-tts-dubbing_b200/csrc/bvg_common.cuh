@@ -46,6 +46,10 @@ struct ConvArgs {
   int max_q;            // max over segments of (len_in + q_extra)
   float out_scale;      // y = (acc + bias + res) * out_scale (+ y_old if accumulate)
   int accumulate;
+  // tcgen05 kernel only: m-tile table (tile = 128*msub rows of q per segment)
+  const int* tile_prefix;   // [B+1] prefix sum of tiles per segment (device)
+  int total_mt;             // tile_prefix[B]
+  int msub;                 // 1 or 2
 };
 
 struct ActArgs {
@@ -106,8 +110,10 @@ template <> __device__ __forceinline__ __half from_f32<__half>(float x) { return
 
 // host-side launchers (each returns cudaGetLastError())
 cudaError_t launch_act_c8(const ActArgs& a, int dtype, bool precise, cudaStream_t s);
+cudaError_t launch_act_c8_v2(const ActArgs& a, int dtype, bool precise, int rt, cudaStream_t s);
 cudaError_t launch_act_nct(const void* x, void* y, const float* alpha, const float* inv_beta, int B, int C,
                            int T, int dtype, cudaStream_t s);
 cudaError_t launch_conv_simt(const ConvArgs& a, int dtype, cudaStream_t s);
 cudaError_t launch_conv_umma(const ConvArgs& a, cudaStream_t s);
 bool conv_umma_supported(const ConvArgs& a);
+int conv_umma_default_msub(const ConvArgs& a);

@@ -1,25 +1,29 @@
 // tcgen05 (5th-gen tensor core) implicit-GEMM 1-D convolution for sm_100a, bf16 in / fp32 accumulate.
+// Version 2: persistent CTAs, 128- or 256-row tiles, multi-stage TMEM accumulators so the epilogue of
+// tile i overlaps the MMAs of tile i+1, optional weight-stationary B operand for the narrow stages.
 //
 // GEMM view (same as bvg_conv_simt.cu):  D[q, n] = sum_tap sum_ci X[q + tap_off[tap], ci] * W[tap][ci][n]
-//   M = 128 time rows per CTA (UMMA_M = 128, cta_group::1), N = BN <= 256 columns per CTA,
-//   K = taps x Cin, walked as k-blocks of KC 8-channel chunks (KC*8 channels) x taps.
+//   M tile = MSUB x 128 time rows (UMMA_M = 128, cta_group::1, MSUB accumulators per tile),
+//   N tile = BN <= 256 columns, K = taps x Cin walked as k-blocks of KC 8-channel chunks x taps.
 //
 // Operand staging (no tensor maps needed -- the HBM layouts ARE the shared-memory images):
-//   A  activations, packed c8 layout [Cin/8][R][8] bf16.  For one k-block the producer issues KC
-//      bulk copies (cp.async.bulk, mbarrier complete_tx) of AR = 128 + span contiguous rows, one per
-//      8-channel chunk, giving the UMMA no-swizzle K-major layout [chunk][row][16 B]:
-//      core matrix = 8 rows x 16 B contiguous, SBO (next 8 rows) = 128 B, LBO (next K chunk) =
-//      ASTRIDE*16 B.  Because rows are 16 B apart, a dilated tap is just a descriptor start-address
-//      shift of tap_off*16 B: the tile (with halo) is loaded ONCE per k-block and reused by all taps.
-//      Zero "same" padding and the tile halo come from the zero guard rows of the packed layout.
+//   A  activations, packed c8 layout [Cin/8][R][8] bf16.  For one k-block the producer issues KC bulk
+//      copies (cp.async.bulk + mbarrier complete_tx) of AROWS = 128*MSUB + span contiguous rows, one
+//      per 8-channel chunk, giving the UMMA no-swizzle K-major layout [chunk][row][16 B]: core matrix
+//      = 8 rows x 16 B contiguous, SBO (next 8 rows) = 128 B, LBO (next K chunk) = ASTRIDE*16 B.
+//      Rows are 16 B apart, so a dilated tap is a descriptor start-address shift of tap_off*16 B and
+//      the second 128-row sub-tile a shift of 128*16 B: the tile (+halo) is loaded ONCE per k-block
+//      and reused by all taps.  Zero padding / halo come from the zero guard rows of the layout.
 //   B  weights, pre-packed by launch_repack_umma into per-(n-tile, k-block, tap) images
-//      [chunk][n][16 B] (same canonical layout, LBO = BN*16 B): one bulk copy per pipeline stage.
-//   D  fp32 accumulator in TMEM (BN columns x 128 lanes); epilogue warps read it with tcgen05.ld
-//      (lane = time row, 8 consecutive columns = one 16-byte c8 vector) and apply
-//      bias / residual / scale / accumulate before a coalesced 16-byte store.
+//      [chunk][n][16 B] (LBO = BN*16 B): one bulk copy per pipeline stage; both sub-tiles reuse it.
+//      When a layer's whole weight slice fits (narrow stages) it is loaded once per CTA and kept.
+//   D  fp32 accumulators in TMEM: ACC stages x MSUB accumulators x BNC columns (<= 512 columns).
 //
-// Warp roles (192 threads): warp 0 = bulk-copy producer, warp 1 = TMEM allocator + MMA issuer
-// (one elected lane), warps 2..5 = epilogue (TMEM lane quarter = warp_id % 4).
+// Warp roles (64 + 32*EPIW threads): warp 0 = bulk-copy producer, warp 1 = TMEM allocator + MMA
+// issuer (one elected lane), warps 2.. = epilogue (TMEM lane quarter = warp_id % 4, the EPIW/4 warps
+// of a quarter split the 8-column chunks).  Epilogue: tcgen05.ld (lane = time row, 8 columns = one
+// 16-byte c8 vector) -> bias / residual / scale / accumulate -> coalesced 16-byte stores, batched 4
+// chunks deep so several residual loads are in flight per thread.
 #include <cstdlib>
 
 #include "bvg_common.cuh"
@@ -27,46 +31,39 @@
 
 namespace {
 
-constexpr int BM = 128;
 constexpr int MAXSPAN = 50;
-constexpr int ASTRIDE = BM + MAXSPAN + 6;   // 184 rows between K chunks of the A stage
-constexpr int NTHREADS = 192;
-constexpr int SMEM_LIMIT = 200 * 1024;
+constexpr int SMEM_BUDGET = 200 * 1024;   // operand stages; barriers etc. come on top
+constexpr int SMEM_MAX = 224 * 1024;
+constexpr int MAX_STAGES = 12;
 
 struct UmmaTiling {
-  int KC;        // 8-channel chunks per k-block
-  int NKB;       // k-blocks
-  int BN;        // columns per CTA (multiple of 16, <= 256)
-  int NT;        // n tiles
-  int tmem_cols; // power of two >= 32
-  int NA, NB;    // pipeline depths
-  size_t a_stage_bytes, b_stage_bytes, smem_bytes;
+  int KC, NKB;      // 8-channel chunks per k-block, k-blocks
+  int BN, NT;       // columns per CTA tile (multiple of 16, <= 256), n tiles
+  int BNC;          // TMEM columns per accumulator (BN rounded up to 32)
   bool ok;
 };
 
-__host__ __device__ inline int round_up_i(int x, int m) { return (x + m - 1) / m * m; }
+inline int round_up_i(int x, int m) { return (x + m - 1) / m * m; }
+inline int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
 
+// Tiling that only depends on the layer (the weight image layout depends on it).
 inline UmmaTiling make_tiling(int ntaps, int Cin, int N) {
   UmmaTiling t{};
   t.ok = false;
   if (Cin % 8 || N % 8 || ntaps < 1 || ntaps > BVG_MAX_TAPS) return t;
   const int cin_pad = round_up_i(Cin, 16);
-  if (cin_pad <= 128) { t.KC = cin_pad / 8; t.NKB = 1; }
-  else if (cin_pad % 64 == 0) { t.KC = 8; t.NKB = cin_pad / 64; }
+  if (cin_pad % 64 == 0) { t.KC = 8; t.NKB = cin_pad / 64; }
+  else if (cin_pad <= 128) { t.KC = cin_pad / 8; t.NKB = 1; }
   else return t;
+  static const int bnmax = [] { int v = env_int("BVG_CONV_BNMAX", 128); return (v == 256 || v == 192) ? v : 128; }();
   const int n_pad = round_up_i(N, 16);
-  t.NT = (n_pad + 255) / 256;
+  t.NT = (n_pad + bnmax - 1) / bnmax;
   t.BN = round_up_i((n_pad + t.NT - 1) / t.NT, 16);
-  t.tmem_cols = 32;
-  while (t.tmem_cols < t.BN) t.tmem_cols <<= 1;
-  t.a_stage_bytes = (size_t)t.KC * ASTRIDE * 16;
-  t.b_stage_bytes = (size_t)t.KC * t.BN * 16;
-  t.NA = t.NKB > 1 ? 2 : 1;
-  const int total_b = t.NKB * ntaps;
-  t.NB = total_b < 4 ? total_b : 4;
-  while (t.NB > 2 && t.NA * t.a_stage_bytes + t.NB * t.b_stage_bytes + 1024 > (size_t)SMEM_LIMIT) --t.NB;
-  t.smem_bytes = t.NA * t.a_stage_bytes + t.NB * t.b_stage_bytes + 1024;
-  t.ok = t.smem_bytes <= (size_t)SMEM_LIMIT;
+  t.BNC = round_up_i(t.BN, 32);
+  t.ok = true;
   return t;
 }
 
@@ -80,6 +77,9 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
@@ -119,14 +119,12 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+__device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // UMMA shared-memory descriptor, SWIZZLE_NONE, K-major: start addr, LBO (K-chunk stride), SBO (8-row
 // group stride), version 1 (Blackwell).  All byte quantities are encoded >> 4.
@@ -141,51 +139,54 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 
 struct UmmaKernelArgs {
   ConvArgs c;
-  int KC, NKB, BN, tmem_cols, NA, NB;
+  const int* tile_prefix;   // [B+1] prefix sum of m-tiles per segment (tile = 128*MSUB rows)
+  int total_mt;             // tile_prefix[B]
+  int KC, NKB, BN, BNC, NT;
+  int MSUB;                 // 128-row sub-tiles per tile (1 or 2)
+  int ACC;                  // TMEM accumulator stages
+  int tmem_cols;
+  int NA, NB;               // smem pipeline depths
+  int EPIW;                 // epilogue warps (4 or 8)
+  int b_resident;           // weights loaded once per CTA (NB == NKB*ntaps, NT == 1)
+  int astride;              // rows between K chunks of an A stage
   int a_stage_bytes, b_stage_bytes;
-  int kc_last_load;   // real (non-padding) chunks of the last k-block
+  int kc_last_load;         // real (non-padding) chunks of the last k-block
   int minoff, span;
-  int swap_lbo_sbo;   // debug knob (BVG_UMMA_SWAP=1): exchange the LBO / SBO descriptor fields
+  int sub_inner;            // issue order: alternate the MSUB accumulators inside the k16 loop
 };
 
-__global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UmmaKernelArgs ka) {
+__global__ void __launch_bounds__(64 + 32 * 8, 1) conv_umma_kernel(const UmmaKernelArgs ka) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const ConvArgs& a = ka.c;
-  const int b = blockIdx.z;
-  const SegDesc si = a.seg_in[b], so = a.seg_out[b];
-  const int q0 = blockIdx.x * BM;
-  const int Lq = si.len + a.q_extra;
-  if (q0 >= Lq) return;
-  const int ntile = blockIdx.y;
-  const int n0 = ntile * ka.BN;
-  const int N = a.u * a.Cout;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_tiles = ka.total_mt * ka.NT;
+  const int TM = 128 * ka.MSUB;
 
-  // smem carve-up: [A stages][B stages][barriers]
+  // smem carve-up: [A stages][B stages][barriers][tmem slot]
   uint8_t* a_smem = smem;
   uint8_t* b_smem = smem + (size_t)ka.NA * ka.a_stage_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(b_smem + (size_t)ka.NB * ka.b_stage_bytes);
-  // bars: [0,NA) a_full, [NA,2NA) a_empty, [2NA, 2NA+NB) b_full, [2NA+NB, 2NA+2NB) b_empty, then tmem_full
   const uint32_t bar0 = smem_u32(bars);
   auto A_FULL = [&](int s) { return bar0 + 8u * s; };
   auto A_EMPTY = [&](int s) { return bar0 + 8u * (ka.NA + s); };
   auto B_FULL = [&](int s) { return bar0 + 8u * (2 * ka.NA + s); };
   auto B_EMPTY = [&](int s) { return bar0 + 8u * (2 * ka.NA + ka.NB + s); };
-  const uint32_t TMEM_FULL = bar0 + 8u * (2 * ka.NA + 2 * ka.NB);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * ka.NA + 2 * ka.NB + 1);
+  auto T_FULL = [&](int s) { return bar0 + 8u * (2 * ka.NA + 2 * ka.NB + s); };
+  auto T_EMPTY = [&](int s) { return bar0 + 8u * (2 * ka.NA + 2 * ka.NB + ka.ACC + s); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * ka.NA + 2 * ka.NB + 2 * ka.ACC);
 
   // padding chunks (Cin not a multiple of 16) must read as zero: clear the A stages once
   if (ka.kc_last_load < ka.KC) {
     uint4 z = make_uint4(0, 0, 0, 0);
     uint4* p = reinterpret_cast<uint4*>(a_smem);
     const int n16 = ka.NA * ka.a_stage_bytes / 16;
-    for (int i = threadIdx.x; i < n16; i += NTHREADS) p[i] = z;
+    for (int i = threadIdx.x; i < n16; i += blockDim.x) p[i] = z;
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (threadIdx.x == 0) {
     for (int s = 0; s < ka.NA; ++s) { mbar_init(A_FULL(s), 1); mbar_init(A_EMPTY(s), 1); }
     for (int s = 0; s < ka.NB; ++s) { mbar_init(B_FULL(s), 1); mbar_init(B_EMPTY(s), 1); }
-    mbar_init(TMEM_FULL, 1);
+    for (int s = 0; s < ka.ACC; ++s) { mbar_init(T_FULL(s), 1); mbar_init(T_EMPTY(s), (uint32_t)ka.EPIW); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), (uint32_t)ka.tmem_cols);
@@ -194,120 +195,213 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UmmaKernel
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int AR = BM + ka.span;   // rows loaded per chunk
+  const int arows = TM + ka.span;          // rows loaded per chunk
+  const int acc_cols = ka.MSUB * ka.BNC;   // TMEM columns per accumulator stage
+
+  // tile id -> (n tile, segment, first row).  Tiles are n-tile-major so that CTAs running at the same
+  // time stream the same slice of the weights (L2 reuse).
+  auto decode = [&](int t, int& nt, int& b, int& q0) {
+    nt = t / ka.total_mt;
+    const int mt = t - nt * ka.total_mt;
+    b = 0;
+    while (mt >= ka.tile_prefix[b + 1]) ++b;
+    q0 = (mt - ka.tile_prefix[b]) * TM;
+  };
 
   if (warp == 0) {
     // ===================== producer =====================
     if (lane == 0) {
       const __nv_bfloat16* xg = reinterpret_cast<const __nv_bfloat16*>(a.x);
       const uint8_t* wimg = reinterpret_cast<const uint8_t*>(a.w);
-      const long long row0 = (long long)si.off + q0 + ka.minoff;
       int sa = 0, pa = 0, sb = 0, pb = 0;
-      for (int kb = 0; kb < ka.NKB; ++kb) {
-        const int kcl = (kb == ka.NKB - 1) ? ka.kc_last_load : ka.KC;
-        mbar_wait(A_EMPTY(sa), pa ^ 1);
-        mbar_expect_tx(A_FULL(sa), (uint32_t)(kcl * AR * 16));
-        const uint32_t adst = smem_u32(a_smem + (size_t)sa * ka.a_stage_bytes);
-        for (int c = 0; c < kcl; ++c) {
-          const __nv_bfloat16* src = xg + ((size_t)(kb * ka.KC + c) * a.Rx + row0) * 8;
-          bulk_g2s(adst + (uint32_t)c * ASTRIDE * 16, src, (uint32_t)(AR * 16), A_FULL(sa));
+      bool first = true;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        int nt, b, q0;
+        decode(t, nt, b, q0);
+        const long long row0 = (long long)a.seg_in[b].off + q0 + ka.minoff;
+        for (int kb = 0; kb < ka.NKB; ++kb) {
+          const int kcl = (kb == ka.NKB - 1) ? ka.kc_last_load : ka.KC;
+          mbar_wait(A_EMPTY(sa), pa ^ 1);
+          mbar_expect_tx(A_FULL(sa), (uint32_t)(kcl * arows * 16));
+          const uint32_t adst = smem_u32(a_smem + (size_t)sa * ka.a_stage_bytes);
+          for (int c = 0; c < kcl; ++c) {
+            const __nv_bfloat16* src = xg + ((size_t)(kb * ka.KC + c) * a.Rx + row0) * 8;
+            bulk_g2s(adst + (uint32_t)(c * ka.astride) * 16, src, (uint32_t)(arows * 16), A_FULL(sa));
+          }
+          if (++sa == ka.NA) { sa = 0; pa ^= 1; }
+          if (!ka.b_resident || first) {
+            for (int tap = 0; tap < a.ntaps; ++tap) {
+              if (!ka.b_resident) mbar_wait(B_EMPTY(sb), pb ^ 1);
+              mbar_expect_tx(B_FULL(sb), (uint32_t)ka.b_stage_bytes);
+              const uint8_t* src = wimg + ((size_t)(nt * ka.NKB + kb) * a.ntaps + tap) * ka.b_stage_bytes;
+              bulk_g2s(smem_u32(b_smem + (size_t)sb * ka.b_stage_bytes), src, (uint32_t)ka.b_stage_bytes, B_FULL(sb));
+              if (++sb == ka.NB) { sb = 0; pb ^= 1; }
+            }
+          }
         }
-        for (int tap = 0; tap < a.ntaps; ++tap) {
-          mbar_wait(B_EMPTY(sb), pb ^ 1);
-          mbar_expect_tx(B_FULL(sb), (uint32_t)ka.b_stage_bytes);
-          const uint8_t* src = wimg + ((size_t)(ntile * ka.NKB + kb) * a.ntaps + tap) * ka.b_stage_bytes;
-          bulk_g2s(smem_u32(b_smem + (size_t)sb * ka.b_stage_bytes), src, (uint32_t)ka.b_stage_bytes, B_FULL(sb));
-          if (++sb == ka.NB) { sb = 0; pb ^= 1; }
-        }
-        if (++sa == ka.NA) { sa = 0; pa ^= 1; }
+        first = false;
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       // instruction descriptor: D=f32, A=B=bf16, both K-major, N=BN, M=128
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(ka.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-      const uint32_t lbo_a = ASTRIDE * 16, lbo_b = (uint32_t)ka.BN * 16;
-      int sa = 0, pa = 0, sb = 0, pb = 0;
-      uint32_t accum = 0;
-      for (int kb = 0; kb < ka.NKB; ++kb) {
-        mbar_wait(A_FULL(sa), pa);
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(ka.BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      const uint32_t lbo_a = (uint32_t)ka.astride * 16, lbo_b = (uint32_t)ka.BN * 16;
+      // Descriptors differ only in the 14-bit start-address field (bits 0-13 of the low word), so the
+      // issue loop is one 32-bit add per operand per MMA: keep the single issuing thread cheap.
+      const uint64_t adesc0 = make_desc(0, lbo_a, 128), bdesc0 = make_desc(0, lbo_b, 128);
+      const uint32_t a_hi = (uint32_t)(adesc0 >> 32), a_lo0 = (uint32_t)adesc0;
+      const uint32_t b_hi = (uint32_t)(bdesc0 >> 32), b_lo0 = (uint32_t)bdesc0;
+      const uint32_t a_kstep = (2u * lbo_a) >> 4, b_kstep = (2u * lbo_b) >> 4;
+      const int nk16 = ka.KC / 2;
+      int sa = 0, pa = 0, sb = 0, pb = 0, acc = 0, pacc = 0;
+      bool first = true;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        mbar_wait(T_EMPTY(acc), pacc ^ 1);   // epilogue has drained this accumulator stage
         tc_fence_after();
-        const uint32_t abase = smem_u32(a_smem + (size_t)sa * ka.a_stage_bytes);
-        for (int tap = 0; tap < a.ntaps; ++tap) {
-          mbar_wait(B_FULL(sb), pb);
+        const uint32_t dbase = tmem_base + (uint32_t)(acc * acc_cols);
+        uint32_t accum = 0;
+        for (int kb = 0; kb < ka.NKB; ++kb) {
+          mbar_wait(A_FULL(sa), pa);
           tc_fence_after();
-          const uint32_t bbase = smem_u32(b_smem + (size_t)sb * ka.b_stage_bytes);
-          const uint32_t ashift = (uint32_t)(a.tap_off[tap] - ka.minoff) * 16;
-          for (int k16 = 0; k16 < ka.KC / 2; ++k16) {
-            const uint32_t aaddr = abase + ashift + (uint32_t)(2 * k16) * lbo_a;
-            const uint32_t baddr = bbase + (uint32_t)(2 * k16) * lbo_b;
-            const uint64_t adesc = ka.swap_lbo_sbo ? make_desc(aaddr, 128, lbo_a) : make_desc(aaddr, lbo_a, 128);
-            const uint64_t bdesc = ka.swap_lbo_sbo ? make_desc(baddr, 128, lbo_b) : make_desc(baddr, lbo_b, 128);
-            umma_bf16(tmem_base, adesc, bdesc, idesc, accum);
+          const uint32_t abase = smem_u32(a_smem + (size_t)sa * ka.a_stage_bytes);
+          for (int tap = 0; tap < a.ntaps; ++tap) {
+            if (!ka.b_resident || first) {
+              mbar_wait(B_FULL(sb), pb);
+              tc_fence_after();
+            }
+            const uint32_t bbase = smem_u32(b_smem + (size_t)sb * ka.b_stage_bytes);
+            const uint32_t a_lo_tap = a_lo0 + ((abase & 0x3FFFFu) >> 4) + (uint32_t)(a.tap_off[tap] - ka.minoff);
+            const uint32_t b_lo_tap = b_lo0 + ((bbase & 0x3FFFFu) >> 4);
+            if (ka.sub_inner && ka.MSUB == 2) {
+              // alternate the two accumulators so consecutive MMAs are independent
+              uint32_t a_lo = a_lo_tap, b_lo = b_lo_tap;
+#pragma unroll 4
+              for (int k16 = 0; k16 < nk16; ++k16) {
+                const uint64_t bdesc = ((uint64_t)b_hi << 32) | b_lo;
+                umma_bf16(dbase, ((uint64_t)a_hi << 32) | a_lo, bdesc, idesc, accum | (uint32_t)k16);
+                umma_bf16(dbase + (uint32_t)ka.BNC, ((uint64_t)a_hi << 32) | (a_lo + 128u), bdesc, idesc,
+                          accum | (uint32_t)k16);
+                a_lo += a_kstep; b_lo += b_kstep;
+              }
+            } else {
+              for (int sub = 0; sub < ka.MSUB; ++sub) {
+                uint32_t a_lo = a_lo_tap + (uint32_t)sub * 128u, b_lo = b_lo_tap;   // +128 rows = +2048 B
+                const uint32_t d = dbase + (uint32_t)(sub * ka.BNC);
+#pragma unroll 4
+                for (int k16 = 0; k16 < nk16; ++k16) {
+                  const uint64_t adesc = ((uint64_t)a_hi << 32) | a_lo, bdesc = ((uint64_t)b_hi << 32) | b_lo;
+                  umma_bf16(d, adesc, bdesc, idesc, accum | (uint32_t)k16);
+                  a_lo += a_kstep; b_lo += b_kstep;
+                }
+              }
+            }
             accum = 1;
+            if (!ka.b_resident) umma_commit(B_EMPTY(sb));
+            if (++sb == ka.NB) { sb = 0; pb ^= 1; }
           }
-          umma_commit(B_EMPTY(sb));
-          if (++sb == ka.NB) { sb = 0; pb ^= 1; }
+          umma_commit(A_EMPTY(sa));
+          if (++sa == ka.NA) { sa = 0; pa ^= 1; }
         }
-        umma_commit(A_EMPTY(sa));
-        if (++sa == ka.NA) { sa = 0; pa ^= 1; }
+        umma_commit(T_FULL(acc));
+        if (++acc == ka.ACC) { acc = 0; pacc ^= 1; }
+        first = false;
       }
-      umma_commit(TMEM_FULL);
     }
   } else {
     // ===================== epilogue =====================
-    const int quarter = warp & 3;
-    const int row = quarter * 32 + lane;
-    const int q = q0 + row;
-    mbar_wait(TMEM_FULL, 0);
-    tc_fence_after();
+    const int e = warp - 2;
+    const int quarter = warp & 3;            // TMEM lanes this warp may touch: 32*quarter ..
+    const int split = e >> 2, nsplit = ka.EPIW >> 2;
+    const int nchunks = ka.BN >> 3;
+    const int N = a.u * a.Cout;
     __nv_bfloat16* yg = reinterpret_cast<__nv_bfloat16*>(a.y);
     const __nv_bfloat16* rg = reinterpret_cast<const __nv_bfloat16*>(a.res);
-    const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    for (int cg = 0; cg < ka.BN; cg += 16) {
-      uint32_t r[16];
-      __syncwarp();   // tcgen05.ld is .sync.aligned: reconverge after the predicated stores below
-      tmem_ld16(trow + (uint32_t)cg, r);
+    int acc = 0, pacc = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      int nt, b, q0;
+      decode(t, nt, b, q0);
+      const SegDesc so = a.seg_out[b];
+      const int Lq = a.seg_in[b].len + a.q_extra;
+      const int n0 = nt * ka.BN;
+      mbar_wait(T_FULL(acc), pacc);
+      tc_fence_after();
+      for (int sub = 0; sub < ka.MSUB; ++sub) {
+        const int q = q0 + sub * 128 + quarter * 32 + lane;
+        const bool qok = q < Lq;
+        const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * acc_cols + sub * ka.BNC);
+        for (int c0 = split; c0 < nchunks; c0 += 4 * nsplit) {
+          uint32_t r[4][8];
+          uint4 resv[4], oldv[4];
+          size_t off[4];
+          bool ok[4];
+          __syncwarp();   // tcgen05.ld is .sync.aligned: reconverge after the predicated stores below
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int n = n0 + cg + 8 * h;
-        if (n >= N) continue;
-        const int phase = n / a.Cout, co = n - phase * a.Cout;
-        const int orow = q * a.u + phase - a.p;
-        if (!(q < Lq && orow >= 0 && orow < so.len)) continue;
-        float v[8];
+          for (int u = 0; u < 4; ++u) {
+            const int c = c0 + u * nsplit;
+            if (c < nchunks) tmem_ld8_nowait(trow + (uint32_t)(c * 8), r[u]);
+          }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[8 * h + j]);
-        if (a.bias) {
-          const float4* bp = reinterpret_cast<const float4*>(a.bias + (size_t)b * a.bias_bstride + co);
-          float4 b0 = bp[0], b1 = bp[1];
-          v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-          v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+          for (int u = 0; u < 4; ++u) {
+            const int c = c0 + u * nsplit;
+            const int n = n0 + c * 8;
+            ok[u] = false;
+            if (c < nchunks && n < N && qok) {
+              const int phase = n / a.Cout, co = n - phase * a.Cout;
+              const int orow = q * a.u + phase - a.p;
+              if (orow >= 0 && orow < so.len) {
+                ok[u] = true;
+                off[u] = ((size_t)(co >> 3) * a.Ry + so.off + orow) * 8;
+                if (rg) resv[u] = *reinterpret_cast<const uint4*>(rg + off[u]);
+                if (a.accumulate) oldv[u] = *reinterpret_cast<const uint4*>(yg + off[u]);
+              }
+            }
+          }
+          tmem_ld_wait();
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (!ok[u]) continue;
+            const int c = c0 + u * nsplit;
+            const int n = n0 + c * 8;
+            const int co = n % a.Cout;
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[u][j]);
+            if (a.bias) {
+              const float4* bp = reinterpret_cast<const float4*>(a.bias + (size_t)b * a.bias_bstride + co);
+              const float4 b0 = bp[0], b1 = bp[1];
+              v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+              v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+            }
+            if (rg) {
+              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&resv[u]);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) { float2 f = __bfloat1622float2(h[j]); v[2 * j] += f.x; v[2 * j + 1] += f.y; }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] *= a.out_scale;
+            if (a.accumulate) {
+              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&oldv[u]);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) { float2 f = __bfloat1622float2(h[j]); v[2 * j] += f.x; v[2 * j + 1] += f.y; }
+            }
+            uint4 o;
+            __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) oh[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+            *reinterpret_cast<uint4*>(yg + off[u]) = o;
+          }
         }
-        const size_t o = ((size_t)(co >> 3) * a.Ry + so.off + orow) * 8;
-        if (rg) {
-          Vec8<__nv_bfloat16> rv;
-          rv.load(rg + o);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] += rv.v[j];
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] *= a.out_scale;
-        if (a.accumulate) {
-          Vec8<__nv_bfloat16> ov;
-          ov.load(yg + o);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] += ov.v[j];
-        }
-        Vec8<__nv_bfloat16> outv;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) outv.v[j] = v[j];
-        outv.store(yg + o);
       }
+      // all of this warp's tcgen05.ld for the stage have completed (wait::ld above): release it
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(T_EMPTY(acc));
+      if (++acc == ka.ACC) { acc = 0; pacc ^= 1; }
     }
-    tc_fence_before();
   }
+  tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     __syncwarp();
@@ -334,12 +428,67 @@ __global__ void repack_umma_kernel(const float* __restrict__ wt, __nv_bfloat16* 
   img[idx] = __float2bfloat16_rn(v);
 }
 
+void tap_range(const ConvArgs& a, int& mn, int& mx) {
+  mn = mx = a.tap_off[0];
+  for (int j = 1; j < a.ntaps; ++j) { mn = a.tap_off[j] < mn ? a.tap_off[j] : mn; mx = a.tap_off[j] > mx ? a.tap_off[j] : mx; }
+}
+
+// Launch-time configuration (depends on the batch geometry as well as on the layer).
+bool configure(const ConvArgs& a, UmmaKernelArgs& ka, size_t& smem_bytes) {
+  const int N = a.u * a.Cout;
+  const UmmaTiling t = make_tiling(a.ntaps, a.Cin, N);
+  if (!t.ok) return false;
+  int mn, mx;
+  tap_range(a, mn, mx);
+  if (mx - mn > MAXSPAN || -mn > BVG_GUARD || mx > BVG_GUARD) return false;
+  ka.c = a;
+  ka.KC = t.KC; ka.NKB = t.NKB; ka.BN = t.BN; ka.BNC = t.BNC; ka.NT = t.NT;
+  ka.minoff = mn; ka.span = mx - mn;
+  ka.MSUB = a.msub == 2 ? 2 : 1;
+  ka.ACC = 512 / (ka.MSUB * ka.BNC);
+  if (ka.ACC > 4) ka.ACC = 4;
+  if (ka.ACC < 1) return false;
+  ka.tmem_cols = 32;
+  while (ka.tmem_cols < ka.ACC * ka.MSUB * ka.BNC) ka.tmem_cols <<= 1;
+  ka.astride = 128 * ka.MSUB + MAXSPAN + 6;
+  ka.a_stage_bytes = t.KC * ka.astride * 16;
+  ka.b_stage_bytes = t.KC * t.BN * 16;
+  ka.kc_last_load = a.Cin / 8 - (t.NKB - 1) * t.KC;
+  static const int sub_inner_env = env_int("BVG_CONV_SUBINNER", 1);
+  ka.sub_inner = sub_inner_env;
+  static const int epiw_env = env_int("BVG_CONV_EPIW", 8);
+  ka.EPIW = epiw_env == 4 ? 4 : 8;
+  // pipeline depths within the smem budget
+  const int total_b = t.NKB * a.ntaps;
+  ka.NA = t.NKB > 1 ? 2 : 3;
+  ka.b_resident = 0;
+  static const int allow_resident = env_int("BVG_CONV_RESIDENT", 1);
+  if (allow_resident && t.NT == 1 && total_b <= MAX_STAGES &&
+      (size_t)ka.NA * ka.a_stage_bytes + (size_t)total_b * ka.b_stage_bytes <= (size_t)SMEM_BUDGET) {
+    ka.b_resident = 1;
+    ka.NB = total_b;
+  } else {
+    int nb = (SMEM_BUDGET - ka.NA * ka.a_stage_bytes) / ka.b_stage_bytes;
+    if (nb > 8) nb = 8;
+    if (nb > total_b) nb = total_b;
+    if (nb < 2 && total_b >= 2) {
+      if (ka.NA > 2) { ka.NA = 2; nb = (SMEM_BUDGET - ka.NA * ka.a_stage_bytes) / ka.b_stage_bytes; }
+      if (nb < 2) return false;
+    }
+    ka.NB = nb;
+  }
+  smem_bytes = (size_t)ka.NA * ka.a_stage_bytes + (size_t)ka.NB * ka.b_stage_bytes +
+               8 * (size_t)(2 * ka.NA + 2 * ka.NB + 2 * ka.ACC) + 16;
+  if (smem_bytes < 120 * 1024) smem_bytes = 120 * 1024;   // one persistent CTA per SM (it owns the TMEM)
+  return smem_bytes <= (size_t)SMEM_MAX;
+}
+
 }  // namespace
 
 size_t umma_weight_image_bytes(int ntaps, int Cin, int N) {
   UmmaTiling t = make_tiling(ntaps, Cin, N);
   if (!t.ok) return 0;
-  return (size_t)t.NT * t.NKB * ntaps * t.b_stage_bytes;
+  return (size_t)t.NT * t.NKB * ntaps * t.KC * t.BN * 16;
 }
 
 cudaError_t launch_repack_umma(const float* wp_tap_major, void* img, int ntaps, int Cin, int N, cudaStream_t s) {
@@ -351,44 +500,35 @@ cudaError_t launch_repack_umma(const float* wp_tap_major, void* img, int ntaps, 
   return cudaGetLastError();
 }
 
-static void tap_range(const ConvArgs& a, int& mn, int& mx) {
-  mn = mx = a.tap_off[0];
-  for (int j = 1; j < a.ntaps; ++j) { mn = a.tap_off[j] < mn ? a.tap_off[j] : mn; mx = a.tap_off[j] > mx ? a.tap_off[j] : mx; }
+int conv_umma_default_msub(const ConvArgs& a) {
+  static const int forced = env_int("BVG_CONV_MSUB", 0);
+  if (forced == 1 || forced == 2) return forced;
+  return a.max_q > 128 ? 2 : 1;
 }
 
 bool conv_umma_supported(const ConvArgs& a) {
-  UmmaTiling t = make_tiling(a.ntaps, a.Cin, a.u * a.Cout);
-  if (!t.ok) return false;
-  int mn, mx;
-  tap_range(a, mn, mx);
-  return (mx - mn) <= MAXSPAN && -mn <= BVG_GUARD && mx <= BVG_GUARD;
+  UmmaKernelArgs ka{};
+  size_t smem;
+  return a.tile_prefix != nullptr && configure(a, ka, smem);
 }
 
 cudaError_t launch_conv_umma(const ConvArgs& a, cudaStream_t s) {
-  if (a.B <= 0 || a.max_q <= 0) return cudaSuccess;
-  const int N = a.u * a.Cout;
-  UmmaTiling t = make_tiling(a.ntaps, a.Cin, N);
-  if (!t.ok) return cudaErrorInvalidValue;
+  if (a.B <= 0 || a.max_q <= 0 || a.total_mt <= 0) return cudaSuccess;
   UmmaKernelArgs ka{};
-  ka.c = a;
-  ka.KC = t.KC; ka.NKB = t.NKB; ka.BN = t.BN; ka.tmem_cols = t.tmem_cols; ka.NA = t.NA; ka.NB = t.NB;
-  ka.a_stage_bytes = (int)t.a_stage_bytes; ka.b_stage_bytes = (int)t.b_stage_bytes;
-  const int real_chunks = a.Cin / 8;
-  ka.kc_last_load = real_chunks - (t.NKB - 1) * t.KC;
-  int mn, mx;
-  tap_range(a, mn, mx);
-  ka.minoff = mn; ka.span = mx - mn;
-  {
-    const char* e = getenv("BVG_UMMA_SWAP");
-    ka.swap_lbo_sbo = (e && e[0] == '1') ? 1 : 0;
+  size_t smem;
+  if (!configure(a, ka, smem)) return cudaErrorInvalidValue;
+  ka.tile_prefix = a.tile_prefix;
+  ka.total_mt = a.total_mt;
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX);
+    if (e != cudaSuccess) { num_sms = 0; return e; }
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
-  dim3 grid((a.max_q + BM - 1) / BM, t.NT, a.B), block(NTHREADS);
-  conv_umma_kernel<<<grid, block, t.smem_bytes, s>>>(ka);
+  const int total_tiles = ka.total_mt * ka.NT;
+  dim3 grid(total_tiles < num_sms ? total_tiles : num_sms), block(64 + 32 * ka.EPIW);
+  conv_umma_kernel<<<grid, block, smem, s>>>(ka);
   return cudaGetLastError();
 }

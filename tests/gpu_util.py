@@ -39,6 +39,15 @@ def activation1d(x, la, lb, dtype=torch.float32):
     return y.float().cpu().numpy()
 
 
+def activation1d_packed(x, la, lb, mode):
+    xt, lat, lbt = dev(x), dev(la), dev(lb)
+    y = torch.empty_like(xt)
+    B, Cc, T = xt.shape
+    lib.check(L_().bvg_activation1d_packed(ptr(xt), ptr(y), ptr(lat), ptr(lbt), B, Cc, T, mode, stream()))
+    torch.cuda.synchronize()
+    return y.cpu().numpy()
+
+
 def conv1d(x, w, b, res, k, d, mode):
     xt, wt = dev(x), dev(w)
     bt = None if b is None else dev(b)

@@ -48,6 +48,23 @@ def test_activation1d_half_types(dtype, tol):
     assert np.abs(y - ref).max() <= tol * max(1.0, np.abs(ref).max())
 
 
+@pytest.mark.parametrize("shape", [(1, 8, 1), (2, 24, 7), (1, 8, 35), (2, 16, 131), (1, 48, 256), (3, 8, 1000),
+                                   (1, 24, 2 * 4096 + 301)])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_activation1d_packed_kernel(shape, mode):
+    """The hot-path kernel (packed c8 layout): interior fast path, sequence ends, short segments."""
+    from tests import gpu_util as G
+    rng = np.random.default_rng(sum(shape))
+    x = (1.5 * rng.standard_normal(shape)).astype(np.float32)
+    la = (0.5 * rng.standard_normal(shape[1])).astype(np.float32)
+    lb = (0.5 * rng.standard_normal(shape[1])).astype(np.float32)
+    xin = x.astype(np.float64) if mode == 0 else G.bf16_round(x)
+    ref = O.activation1d(xin, la.astype(np.float64), lb.astype(np.float64))
+    y = G.activation1d_packed(x, la, lb, mode)
+    tol = 2e-5 if mode == 0 else 2e-2 * max(1.0, np.abs(ref).max())
+    assert np.abs(y - ref).max() <= tol, np.abs(y - ref).max()
+
+
 def test_activation1d_empty_is_noop():
     from tests import gpu_util as G
     from b200vgan import lib
