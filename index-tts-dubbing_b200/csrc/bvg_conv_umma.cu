@@ -116,6 +116,20 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
       : "memory");
 }
+// elect.sync: one lane of the (converged) warp; unlike `lane == 0` it tells ptxas that the guarded
+// region runs with a single active thread, so uniform-datapath code is generated for it.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 rx;\n\t"
+      ".reg .pred px;\n\t"
+      "elect.sync rx|px, 0xffffffff;\n\t"
+      "@px mov.s32 %0, 1;\n\t"
+      "}"
+      : "+r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -137,6 +151,69 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   return d;
 }
 
+// Epilogue of one 128-row accumulator for the plain-convolution case (u == 1): the thread's row is
+// fixed, consecutive 8-column chunks are `cs` elements apart in the packed c8 output, so the loop is
+// pointer bumps + 16-byte accesses.  `nload` chunks exist in TMEM, `nvalid` of them are real columns.
+template <bool RES, bool ACCUM>
+__device__ __forceinline__ void epilogue_rows(uint32_t trow, __nv_bfloat16* yp, const __nv_bfloat16* rp, size_t cs,
+                                              const float* bias, float scale, bool valid, int split, int nsplit,
+                                              int nload, int nvalid) {
+  for (int c0 = split; c0 < nload; c0 += 4 * nsplit) {
+    uint32_t r[4][8];
+    uint4 resv[4], oldv[4];
+    __syncwarp();   // tcgen05.ld is .sync.aligned: reconverge after the predicated stores below
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int c = min(c0 + u * nsplit, nload - 1);   // clamp: always a legal column, result unused if past the end
+      tmem_ld8_nowait(trow + (uint32_t)(c * 8), r[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int c = c0 + u * nsplit;
+      if (valid && c < nvalid) {
+        if (RES) resv[u] = *reinterpret_cast<const uint4*>(rp + (size_t)c * cs);
+        if (ACCUM) oldv[u] = *reinterpret_cast<const uint4*>(yp + (size_t)c * cs);
+      }
+    }
+    tmem_ld_wait();
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int c = c0 + u * nsplit;
+      if (!(valid && c < nvalid)) continue;
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[u][j]);
+      if (bias) {   // same address for the whole warp: one broadcast L1 transaction
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c * 8));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + c * 8 + 4));
+        v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+        v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+      }
+      if (RES) {
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&resv[u]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { float2 f = __bfloat1622float2(h[j]); v[2 * j] += f.x; v[2 * j + 1] += f.y; }
+      }
+      if (ACCUM) {
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&oldv[u]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float2 f = __bfloat1622float2(h[j]);
+          v[2 * j] = fmaf(v[2 * j], scale, f.x); v[2 * j + 1] = fmaf(v[2 * j + 1], scale, f.y);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] *= scale;
+      }
+      uint4 o;
+      __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) oh[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+      *reinterpret_cast<uint4*>(yp + (size_t)c * cs) = o;
+    }
+  }
+}
+
 struct UmmaKernelArgs {
   ConvArgs c;
   const int* tile_prefix;   // [B+1] prefix sum of m-tiles per segment (tile = 128*MSUB rows)
@@ -152,7 +229,6 @@ struct UmmaKernelArgs {
   int a_stage_bytes, b_stage_bytes;
   int kc_last_load;         // real (non-padding) chunks of the last k-block
   int minoff, span;
-  int sub_inner;            // issue order: alternate the MSUB accumulators inside the k16 loop
 };
 
 __global__ void __launch_bounds__(64 + 32 * 8, 1) conv_umma_kernel(const UmmaKernelArgs ka) {
@@ -244,69 +320,61 @@ __global__ void __launch_bounds__(64 + 32 * 8, 1) conv_umma_kernel(const UmmaKer
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // The WHOLE warp runs the loops so every address / descriptor computation is warp-uniform and the
+    // compiler keeps it in uniform registers (tcgen05.mma takes its descriptors from URs; computing them
+    // in a divergent single-lane region costs an R2UR round trip per operand per MMA -- measured with
+    // tools/umma_bench.cu: ~124 cycles per MMA instead of the N/2-cycle floor).  Only the tcgen05
+    // instructions themselves are predicated on one elected lane.
+    {
       // instruction descriptor: D=f32, A=B=bf16, both K-major, N=BN, M=128
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(ka.BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       const uint32_t lbo_a = (uint32_t)ka.astride * 16, lbo_b = (uint32_t)ka.BN * 16;
-      // Descriptors differ only in the 14-bit start-address field (bits 0-13 of the low word), so the
-      // issue loop is one 32-bit add per operand per MMA: keep the single issuing thread cheap.
+      // Descriptors differ only in the 14-bit start-address field (bits 0-13 of the low word).
       const uint64_t adesc0 = make_desc(0, lbo_a, 128), bdesc0 = make_desc(0, lbo_b, 128);
-      const uint32_t a_hi = (uint32_t)(adesc0 >> 32), a_lo0 = (uint32_t)adesc0;
-      const uint32_t b_hi = (uint32_t)(bdesc0 >> 32), b_lo0 = (uint32_t)bdesc0;
       const uint32_t a_kstep = (2u * lbo_a) >> 4, b_kstep = (2u * lbo_b) >> 4;
       const int nk16 = ka.KC / 2;
+      const uint32_t a_smem_lo = (smem_u32(a_smem) & 0x3FFFFu) >> 4, b_smem_lo = (smem_u32(b_smem) & 0x3FFFFu) >> 4;
+      const uint32_t a_stage_lo = (uint32_t)ka.a_stage_bytes >> 4, b_stage_lo = (uint32_t)ka.b_stage_bytes >> 4;
+      const bool two = ka.MSUB == 2;
       int sa = 0, pa = 0, sb = 0, pb = 0, acc = 0, pacc = 0;
       bool first = true;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         mbar_wait(T_EMPTY(acc), pacc ^ 1);   // epilogue has drained this accumulator stage
         tc_fence_after();
-        const uint32_t dbase = tmem_base + (uint32_t)(acc * acc_cols);
+        const uint32_t d0 = tmem_base + (uint32_t)(acc * acc_cols), d1 = d0 + (uint32_t)ka.BNC;
         uint32_t accum = 0;
         for (int kb = 0; kb < ka.NKB; ++kb) {
           mbar_wait(A_FULL(sa), pa);
           tc_fence_after();
-          const uint32_t abase = smem_u32(a_smem + (size_t)sa * ka.a_stage_bytes);
+          const uint64_t adesc_stage = adesc0 + (a_smem_lo + (uint32_t)sa * a_stage_lo);
           for (int tap = 0; tap < a.ntaps; ++tap) {
             if (!ka.b_resident || first) {
               mbar_wait(B_FULL(sb), pb);
               tc_fence_after();
             }
-            const uint32_t bbase = smem_u32(b_smem + (size_t)sb * ka.b_stage_bytes);
-            const uint32_t a_lo_tap = a_lo0 + ((abase & 0x3FFFFu) >> 4) + (uint32_t)(a.tap_off[tap] - ka.minoff);
-            const uint32_t b_lo_tap = b_lo0 + ((bbase & 0x3FFFFu) >> 4);
-            if (ka.sub_inner && ka.MSUB == 2) {
-              // alternate the two accumulators so consecutive MMAs are independent
-              uint32_t a_lo = a_lo_tap, b_lo = b_lo_tap;
-#pragma unroll 4
+            uint64_t adesc = adesc_stage + (uint32_t)(a.tap_off[tap] - ka.minoff);   // row shift of this tap (>= 0)
+            uint64_t bdesc = bdesc0 + (b_smem_lo + (uint32_t)sb * b_stage_lo);
+            // alternate the two accumulators so consecutive MMAs are independent
+            if (elect_one()) {   // single-thread region: descriptors live in uniform registers across the loop
+#pragma unroll 2
               for (int k16 = 0; k16 < nk16; ++k16) {
-                const uint64_t bdesc = ((uint64_t)b_hi << 32) | b_lo;
-                umma_bf16(dbase, ((uint64_t)a_hi << 32) | a_lo, bdesc, idesc, accum | (uint32_t)k16);
-                umma_bf16(dbase + (uint32_t)ka.BNC, ((uint64_t)a_hi << 32) | (a_lo + 128u), bdesc, idesc,
-                          accum | (uint32_t)k16);
-                a_lo += a_kstep; b_lo += b_kstep;
+                umma_bf16(d0, adesc, bdesc, idesc, accum | (uint32_t)k16);
+                if (two) umma_bf16(d1, adesc + 128u, bdesc, idesc, accum | (uint32_t)k16);   // +128 rows
+                adesc += a_kstep; bdesc += b_kstep;
               }
-            } else {
-              for (int sub = 0; sub < ka.MSUB; ++sub) {
-                uint32_t a_lo = a_lo_tap + (uint32_t)sub * 128u, b_lo = b_lo_tap;   // +128 rows = +2048 B
-                const uint32_t d = dbase + (uint32_t)(sub * ka.BNC);
-#pragma unroll 4
-                for (int k16 = 0; k16 < nk16; ++k16) {
-                  const uint64_t adesc = ((uint64_t)a_hi << 32) | a_lo, bdesc = ((uint64_t)b_hi << 32) | b_lo;
-                  umma_bf16(d, adesc, bdesc, idesc, accum | (uint32_t)k16);
-                  a_lo += a_kstep; b_lo += b_kstep;
-                }
-              }
+              if (!ka.b_resident) umma_commit(B_EMPTY(sb));
             }
+            __syncwarp();
             accum = 1;
-            if (!ka.b_resident) umma_commit(B_EMPTY(sb));
             if (++sb == ka.NB) { sb = 0; pb ^= 1; }
           }
-          umma_commit(A_EMPTY(sa));
+          if (elect_one()) umma_commit(A_EMPTY(sa));
           if (++sa == ka.NA) { sa = 0; pa ^= 1; }
         }
-        umma_commit(T_FULL(acc));
+        if (elect_one()) umma_commit(T_FULL(acc));
         if (++acc == ka.ACC) { acc = 0; pacc ^= 1; }
         first = false;
+        __syncwarp();
       }
     }
   } else {
@@ -331,6 +399,22 @@ __global__ void __launch_bounds__(64 + 32 * 8, 1) conv_umma_kernel(const UmmaKer
         const int q = q0 + sub * 128 + quarter * 32 + lane;
         const bool qok = q < Lq;
         const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * acc_cols + sub * ka.BNC);
+        if (a.u == 1) {
+          // plain convolution: output row == q, column n == channel
+          const bool valid = qok && q < so.len;
+          const size_t base = ((size_t)(n0 >> 3) * a.Ry + so.off + q) * 8, cs = (size_t)a.Ry * 8;
+          const float* bias = a.bias ? a.bias + (size_t)b * a.bias_bstride + n0 : nullptr;
+          int nvalid = (N - n0 + 7) >> 3;
+          nvalid = nvalid < nchunks ? nvalid : nchunks;
+          if (rg) {
+            if (a.accumulate) epilogue_rows<true, true>(trow, yg + base, rg + base, cs, bias, a.out_scale, valid, split, nsplit, nchunks, nvalid);
+            else epilogue_rows<true, false>(trow, yg + base, rg + base, cs, bias, a.out_scale, valid, split, nsplit, nchunks, nvalid);
+          } else {
+            if (a.accumulate) epilogue_rows<false, true>(trow, yg + base, nullptr, cs, bias, a.out_scale, valid, split, nsplit, nchunks, nvalid);
+            else epilogue_rows<false, false>(trow, yg + base, nullptr, cs, bias, a.out_scale, valid, split, nsplit, nchunks, nvalid);
+          }
+          continue;
+        }
         for (int c0 = split; c0 < nchunks; c0 += 4 * nsplit) {
           uint32_t r[4][8];
           uint4 resv[4], oldv[4];
@@ -339,8 +423,8 @@ __global__ void __launch_bounds__(64 + 32 * 8, 1) conv_umma_kernel(const UmmaKer
           __syncwarp();   // tcgen05.ld is .sync.aligned: reconverge after the predicated stores below
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            const int c = c0 + u * nsplit;
-            if (c < nchunks) tmem_ld8_nowait(trow + (uint32_t)(c * 8), r[u]);
+            const int c = min(c0 + u * nsplit, nchunks - 1);   // clamped: always a legal column
+            tmem_ld8_nowait(trow + (uint32_t)(c * 8), r[u]);
           }
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
@@ -454,8 +538,6 @@ bool configure(const ConvArgs& a, UmmaKernelArgs& ka, size_t& smem_bytes) {
   ka.a_stage_bytes = t.KC * ka.astride * 16;
   ka.b_stage_bytes = t.KC * t.BN * 16;
   ka.kc_last_load = a.Cin / 8 - (t.NKB - 1) * t.KC;
-  static const int sub_inner_env = env_int("BVG_CONV_SUBINNER", 1);
-  ka.sub_inner = sub_inner_env;
   static const int epiw_env = env_int("BVG_CONV_EPIW", 8);
   ka.EPIW = epiw_env == 4 ? 4 : 8;
   // pipeline depths within the smem budget
@@ -464,9 +546,11 @@ bool configure(const ConvArgs& a, UmmaKernelArgs& ka, size_t& smem_bytes) {
   ka.b_resident = 0;
   static const int allow_resident = env_int("BVG_CONV_RESIDENT", 1);
   if (allow_resident && t.NT == 1 && total_b <= MAX_STAGES &&
-      (size_t)ka.NA * ka.a_stage_bytes + (size_t)total_b * ka.b_stage_bytes <= (size_t)SMEM_BUDGET) {
+      (size_t)2 * ka.a_stage_bytes + (size_t)total_b * ka.b_stage_bytes <= (size_t)SMEM_BUDGET) {
     ka.b_resident = 1;
     ka.NB = total_b;
+    int na = (int)((SMEM_BUDGET - (size_t)total_b * ka.b_stage_bytes) / ka.a_stage_bytes);
+    ka.NA = na > 4 ? 4 : na;   // >= 2 by the test above
   } else {
     int nb = (SMEM_BUDGET - ka.NA * ka.a_stage_bytes) / ka.b_stage_bytes;
     if (nb > 8) nb = 8;
