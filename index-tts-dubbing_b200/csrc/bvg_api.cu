@@ -141,8 +141,8 @@ struct bvg_plan {
   std::vector<int> R, maxlen, C;
   std::vector<long long> sumlen;   // valid rows over all segments, per geometry
   SegDesc* seg_dev = nullptr;   // [(nups+1)][B]
-  int* prefix_dev = nullptr;    // m-tile prefix tables [g][msub-1][q_extra][B+1]
-  std::vector<int> total_mt;    // [g][msub-1][q_extra]
+  int* prefix_dev = nullptr;    // m-tile prefix tables [g][msub in 1,2,4][q_extra][B+1]
+  std::vector<int> total_mt;    // [g][msub in 1,2,4][q_extra]
   size_t ws_bytes = 0;
   size_t off_lat = 0, off_pre = 0, off_bias = 0;
   std::vector<size_t> off_U, off_X, off_A, off_Y, off_XS;
@@ -189,7 +189,7 @@ ConvArgs make_conv_args(const ConvLayer& L, const bvg_plan* p, int gin, int gout
   a.B = p->B; a.max_q = p->maxlen[gin] + L.q_extra;
   a.out_scale = scale; a.accumulate = accumulate;
   a.msub = conv_umma_default_msub(a);
-  const int ti = (gin * 2 + (a.msub - 1)) * 2 + (L.q_extra ? 1 : 0);
+  const int ti = (gin * 3 + (a.msub == 4 ? 2 : a.msub - 1)) * 2 + (L.q_extra ? 1 : 0);
   a.tile_prefix = p->prefix_dev + (size_t)ti * (p->B + 1);
   a.total_mt = p->total_mt[ti];
   return a;
@@ -440,12 +440,13 @@ int bvg_plan_create(bvg_handle* h, int32_t B, const int32_t* frames, int32_t mod
     return fail("bvg_plan_create: segment table upload failed");
   }
   {
-    std::vector<int> pref((size_t)ng * 4 * (B + 1));
-    p->total_mt.assign((size_t)ng * 4, 0);
+    std::vector<int> pref((size_t)ng * 6 * (B + 1));
+    p->total_mt.assign((size_t)ng * 6, 0);
     for (int g = 0; g < ng; ++g)
-      for (int ms = 1; ms <= 2; ++ms)
+      for (int mi = 0; mi < 3; ++mi)
         for (int qe = 0; qe < 2; ++qe) {
-          const int ti = (g * 2 + (ms - 1)) * 2 + qe;
+          const int ms = 1 << mi;   // 128-row sub-tiles per tile: 1, 2, 4
+          const int ti = (g * 3 + mi) * 2 + qe;
           int* pf = pref.data() + (size_t)ti * (B + 1);
           pf[0] = 0;
           for (int b = 0; b < B; ++b) pf[b + 1] = pf[b] + (seg[(size_t)g * B + b].len + qe + 128 * ms - 1) / (128 * ms);

@@ -19,7 +19,7 @@
 #include <stdint.h>
 
 #define BVG_GUARD 32          // zero rows between segments (>= max conv halo 25 + act halo 5)
-#define BVG_TAIL_SLACK 320    // extra zero rows after the last segment (tile overrun of loads)
+#define BVG_TAIL_SLACK 640    // extra zero rows after the last segment (tile overrun of loads: up to 512 + halo)
 #define BVG_MAX_TAPS 11
 
 struct SegDesc {   // one per (stage, segment)
@@ -49,7 +49,7 @@ struct ConvArgs {
   // tcgen05 kernel only: m-tile table (tile = 128*msub rows of q per segment)
   const int* tile_prefix;   // [B+1] prefix sum of tiles per segment (device)
   int total_mt;             // tile_prefix[B]
-  int msub;                 // 1 or 2
+  int msub;                 // 1, 2 or 4
 };
 
 struct ActArgs {

@@ -1,6 +1,7 @@
 // tcgen05 (5th-gen tensor core) implicit-GEMM 1-D convolution for sm_100a, bf16 in / fp32 accumulate.
-// Version 2: persistent CTAs, 128- or 256-row tiles, multi-stage TMEM accumulators so the epilogue of
-// tile i overlaps the MMAs of tile i+1, optional weight-stationary B operand for the narrow stages.
+// Version 3: persistent CTAs, 128/256/512-row tiles, multi-stage TMEM accumulators (the epilogue of
+// tile i overlaps the MMAs of tile i+1), weight-stationary B operand for the narrow stages, a
+// single-thread uniform-datapath MMA issuer and a 32-column-at-a-time epilogue.
 //
 // GEMM view (same as bvg_conv_simt.cu):  D[q, n] = sum_tap sum_ci X[q + tap_off[tap], ci] * W[tap][ci][n]
 //   M tile = MSUB x 128 time rows (UMMA_M = 128, cta_group::1, MSUB accumulators per tile),
@@ -12,18 +13,25 @@
 //      per 8-channel chunk, giving the UMMA no-swizzle K-major layout [chunk][row][16 B]: core matrix
 //      = 8 rows x 16 B contiguous, SBO (next 8 rows) = 128 B, LBO (next K chunk) = ASTRIDE*16 B.
 //      Rows are 16 B apart, so a dilated tap is a descriptor start-address shift of tap_off*16 B and
-//      the second 128-row sub-tile a shift of 128*16 B: the tile (+halo) is loaded ONCE per k-block
+//      the s-th 128-row sub-tile a shift of s*128*16 B: the tile (+halo) is loaded ONCE per k-block
 //      and reused by all taps.  Zero padding / halo come from the zero guard rows of the layout.
 //   B  weights, pre-packed by launch_repack_umma into per-(n-tile, k-block, tap) images
-//      [chunk][n][16 B] (LBO = BN*16 B): one bulk copy per pipeline stage; both sub-tiles reuse it.
+//      [chunk][n][16 B] (LBO = BN*16 B): one bulk copy per pipeline stage; all sub-tiles reuse it.
 //      When a layer's whole weight slice fits (narrow stages) it is loaded once per CTA and kept.
 //   D  fp32 accumulators in TMEM: ACC stages x MSUB accumulators x BNC columns (<= 512 columns).
 //
-// Warp roles (64 + 32*EPIW threads): warp 0 = bulk-copy producer, warp 1 = TMEM allocator + MMA
-// issuer (one elected lane), warps 2.. = epilogue (TMEM lane quarter = warp_id % 4, the EPIW/4 warps
-// of a quarter split the 8-column chunks).  Epilogue: tcgen05.ld (lane = time row, 8 columns = one
-// 16-byte c8 vector) -> bias / residual / scale / accumulate -> coalesced 16-byte stores, batched 4
-// chunks deep so several residual loads are in flight per thread.
+// Warp roles (320 threads): warp 0 = bulk-copy producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2..9 = epilogue (TMEM lane quarter = warp_id % 4; the two warps of a quarter alternate over
+// the (sub-tile, 32-column group) work items).
+//
+// What the measurements behind this structure were (tools/umma_bench.cu, profiles/r1_umma_*):
+//   * one M=128 MMA costs max(N/2, ~40..50) cycles when issued from uniform registers, but ~124 when
+//     its descriptors are built in a divergent single-lane region (R2UR per operand) -> the issuer is
+//     ONE thread chosen with elect.sync (ptxas then emits uniform-datapath code for the whole loop);
+//   * consecutive MMAs into the same accumulator serialise -> the sub-tile loop is innermost;
+//   * narrow stages are bound by per-tile fixed costs (barrier round trips, tile decode, epilogue
+//     latency), not by MMA or HBM -> big tiles (MSUB = 4), x32 TMEM loads, decode prefetch.
+#include <cstdio>
 #include <cstdlib>
 
 #include "bvg_common.cuh"
@@ -35,6 +43,8 @@ constexpr int MAXSPAN = 50;
 constexpr int SMEM_BUDGET = 200 * 1024;   // operand stages; barriers etc. come on top
 constexpr int SMEM_MAX = 224 * 1024;
 constexpr int MAX_STAGES = 12;
+constexpr int EPIW = 8;                   // epilogue warps
+constexpr int NTHREADS = 64 + 32 * EPIW;
 
 struct UmmaTiling {
   int KC, NKB;      // 8-channel chunks per k-block, k-blocks
@@ -58,7 +68,9 @@ inline UmmaTiling make_tiling(int ntaps, int Cin, int N) {
   if (cin_pad % 64 == 0) { t.KC = 8; t.NKB = cin_pad / 64; }
   else if (cin_pad <= 128) { t.KC = cin_pad / 8; t.NKB = 1; }
   else return t;
-  static const int bnmax = [] { int v = env_int("BVG_CONV_BNMAX", 128); return (v == 256 || v == 192) ? v : 128; }();
+  // N tile: 256 columns by default -- a 128 x 256 x 16 MMA is the only cta_group::1 shape that runs at
+  // the tensor-pipe floor (tools/umma_bench.cu) and it halves the A-tile re-reads per output column.
+  static const int bnmax = [] { int v = env_int("BVG_CONV_BNMAX", 256); return (v == 128 || v == 192) ? v : 256; }();
   const int n_pad = round_up_i(N, 16);
   t.NT = (n_pad + bnmax - 1) / bnmax;
   t.BN = round_up_i((n_pad + t.NT - 1) / t.NT, 16);
@@ -133,10 +145,16 @@ __device__ __forceinline__ bool elect_one() {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-__device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t (&r)[8]) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-               : "r"(taddr));
+// 32 lanes x 32 consecutive fp32 columns: thread = lane (time row), r[j] = column j
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
@@ -151,66 +169,35 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   return d;
 }
 
-// Epilogue of one 128-row accumulator for the plain-convolution case (u == 1): the thread's row is
-// fixed, consecutive 8-column chunks are `cs` elements apart in the packed c8 output, so the loop is
-// pointer bumps + 16-byte accesses.  `nload` chunks exist in TMEM, `nvalid` of them are real columns.
-template <bool RES, bool ACCUM>
-__device__ __forceinline__ void epilogue_rows(uint32_t trow, __nv_bfloat16* yp, const __nv_bfloat16* rp, size_t cs,
-                                              const float* bias, float scale, bool valid, int split, int nsplit,
-                                              int nload, int nvalid) {
-  for (int c0 = split; c0 < nload; c0 += 4 * nsplit) {
-    uint32_t r[4][8];
-    uint4 resv[4], oldv[4];
-    __syncwarp();   // tcgen05.ld is .sync.aligned: reconverge after the predicated stores below
+__device__ __forceinline__ void unpack_add(const uint4& p, float (&v)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&p);
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int c = min(c0 + u * nsplit, nload - 1);   // clamp: always a legal column, result unused if past the end
-      tmem_ld8_nowait(trow + (uint32_t)(c * 8), r[u]);
+  for (int j = 0; j < 4; ++j) { float2 f = __bfloat1622float2(h[j]); v[2 * j] += f.x; v[2 * j + 1] += f.y; }
+}
+__device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
+  uint4 o;
+  __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) oh[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+  return o;
+}
+
+// MMAs of one (k-block, tap): nk16 K-steps x MS sub-tile accumulators, sub-tile loop innermost so that
+// consecutive MMAs go to different accumulators.  MS is a compile-time constant to keep the single
+// issuing thread's loop branch-free.
+template <int MS>
+__device__ __forceinline__ void issue_tap(uint32_t d0, uint32_t bnc, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accum, int nk16, uint32_t a_kstep, uint32_t b_kstep) {
+#pragma unroll 4
+  for (int k16 = 0; k16 < nk16; ++k16) {
+    const uint32_t af = accum | (uint32_t)k16;
+    umma_bf16(d0, adesc, bdesc, idesc, af);
+    if (MS >= 2) umma_bf16(d0 + bnc, adesc + 128u, bdesc, idesc, af);   // +128 rows
+    if (MS == 4) {
+      umma_bf16(d0 + 2 * bnc, adesc + 256u, bdesc, idesc, af);
+      umma_bf16(d0 + 3 * bnc, adesc + 384u, bdesc, idesc, af);
     }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int c = c0 + u * nsplit;
-      if (valid && c < nvalid) {
-        if (RES) resv[u] = *reinterpret_cast<const uint4*>(rp + (size_t)c * cs);
-        if (ACCUM) oldv[u] = *reinterpret_cast<const uint4*>(yp + (size_t)c * cs);
-      }
-    }
-    tmem_ld_wait();
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int c = c0 + u * nsplit;
-      if (!(valid && c < nvalid)) continue;
-      float v[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[u][j]);
-      if (bias) {   // same address for the whole warp: one broadcast L1 transaction
-        const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c * 8));
-        const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + c * 8 + 4));
-        v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-        v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-      }
-      if (RES) {
-        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&resv[u]);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) { float2 f = __bfloat1622float2(h[j]); v[2 * j] += f.x; v[2 * j + 1] += f.y; }
-      }
-      if (ACCUM) {
-        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&oldv[u]);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float2 f = __bfloat1622float2(h[j]);
-          v[2 * j] = fmaf(v[2 * j], scale, f.x); v[2 * j + 1] = fmaf(v[2 * j + 1], scale, f.y);
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] *= scale;
-      }
-      uint4 o;
-      __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) oh[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-      *reinterpret_cast<uint4*>(yp + (size_t)c * cs) = o;
-    }
+    adesc += a_kstep; bdesc += b_kstep;
   }
 }
 
@@ -219,19 +206,22 @@ struct UmmaKernelArgs {
   const int* tile_prefix;   // [B+1] prefix sum of m-tiles per segment (tile = 128*MSUB rows)
   int total_mt;             // tile_prefix[B]
   int KC, NKB, BN, BNC, NT;
-  int MSUB;                 // 128-row sub-tiles per tile (1 or 2)
+  int MSUB;                 // 128-row sub-tiles per tile (1, 2 or 4)
   int ACC;                  // TMEM accumulator stages
   int tmem_cols;
   int NA, NB;               // smem pipeline depths
-  int EPIW;                 // epilogue warps (4 or 8)
   int b_resident;           // weights loaded once per CTA (NB == NKB*ntaps, NT == 1)
   int astride;              // rows between K chunks of an A stage
   int a_stage_bytes, b_stage_bytes;
   int kc_last_load;         // real (non-padding) chunks of the last k-block
   int minoff, span;
+  unsigned long long* trace;   // optional event trace of CTA 0 (BVG_CONV_TRACE), nullptr normally
+  int debug;                // tuning aid (BVG_CONV_DEBUG): 1 = epilogue skips global memory, 2 = no MMAs, 4 = no A loads
 };
 
-__global__ void __launch_bounds__(64 + 32 * 8, 1) conv_umma_kernel(const UmmaKernelArgs ka) {
+struct TileRef { int nt, b, q0; };
+
+__global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UmmaKernelArgs ka) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const ConvArgs& a = ka.c;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -262,7 +252,7 @@ __global__ void __launch_bounds__(64 + 32 * 8, 1) conv_umma_kernel(const UmmaKer
   if (threadIdx.x == 0) {
     for (int s = 0; s < ka.NA; ++s) { mbar_init(A_FULL(s), 1); mbar_init(A_EMPTY(s), 1); }
     for (int s = 0; s < ka.NB; ++s) { mbar_init(B_FULL(s), 1); mbar_init(B_EMPTY(s), 1); }
-    for (int s = 0; s < ka.ACC; ++s) { mbar_init(T_FULL(s), 1); mbar_init(T_EMPTY(s), (uint32_t)ka.EPIW); }
+    for (int s = 0; s < ka.ACC; ++s) { mbar_init(T_FULL(s), 1); mbar_init(T_EMPTY(s), (uint32_t)EPIW); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), (uint32_t)ka.tmem_cols);
@@ -271,38 +261,66 @@ __global__ void __launch_bounds__(64 + 32 * 8, 1) conv_umma_kernel(const UmmaKer
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // low-overhead event trace (CTA 0 only): per-role ring in shared memory, flushed at kernel end
+  unsigned long long* tr_smem = reinterpret_cast<unsigned long long*>(smem + (SMEM_MAX - 3 * 1024 * 8));
+  int tr_n = 0;
+  auto TRACE = [&](int role, int ev, int tile) {
+    if (ka.trace && blockIdx.x == 0 && tr_n < 1024) {
+      tr_smem[role * 1024 + tr_n] = ((unsigned long long)ev << 56) | ((unsigned long long)(tile & 0xffff) << 40) | (clock64() & 0xffffffffffULL);
+      ++tr_n;
+    }
+  };
   const int arows = TM + ka.span;          // rows loaded per chunk
   const int acc_cols = ka.MSUB * ka.BNC;   // TMEM columns per accumulator stage
 
   // tile id -> (n tile, segment, first row).  Tiles are n-tile-major so that CTAs running at the same
-  // time stream the same slice of the weights (L2 reuse).
-  auto decode = [&](int t, int& nt, int& b, int& q0) {
-    nt = t / ka.total_mt;
-    const int mt = t - nt * ka.total_mt;
-    b = 0;
-    while (mt >= ka.tile_prefix[b + 1]) ++b;
-    q0 = (mt - ka.tile_prefix[b]) * TM;
+  // time stream the same slice of the weights (L2 reuse).  Each role walks its tiles in increasing
+  // order, so the segment lookup is incremental; roles decode the NEXT tile before they block on a
+  // barrier so the table loads are off the critical path.
+  int dec_nt = -1, dec_b = 0;
+  auto decode = [&](int t) {
+    TileRef r;
+    r.nt = t / ka.total_mt;
+    const int mt = t - r.nt * ka.total_mt;
+    if (r.nt != dec_nt) { dec_nt = r.nt; dec_b = 0; }
+    while (mt >= __ldg(ka.tile_prefix + dec_b + 1)) ++dec_b;
+    r.b = dec_b;
+    r.q0 = (mt - __ldg(ka.tile_prefix + dec_b)) * TM;
+    return r;
   };
 
   if (warp == 0) {
-    // ===================== producer =====================
-    if (lane == 0) {
+    // ===================== producer (one thread) =====================
+    if (elect_one()) {
       const __nv_bfloat16* xg = reinterpret_cast<const __nv_bfloat16*>(a.x);
       const uint8_t* wimg = reinterpret_cast<const uint8_t*>(a.w);
       int sa = 0, pa = 0, sb = 0, pb = 0;
       bool first = true;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        int nt, b, q0;
-        decode(t, nt, b, q0);
-        const long long row0 = (long long)a.seg_in[b].off + q0 + ka.minoff;
+      int t = blockIdx.x;
+      TileRef cur = t < total_tiles ? decode(t) : TileRef{0, 0, 0};
+      long long row0 = t < total_tiles ? (long long)a.seg_in[cur.b].off + cur.q0 + ka.minoff : 0;
+      while (t < total_tiles) {
+        TRACE(0, 0, t);
+        const int tn = t + gridDim.x;
+        const int nt = cur.nt;
+        const long long row0c = row0;
+        if (tn < total_tiles) {   // prefetch the next tile's coordinates
+          cur = decode(tn);
+          row0 = (long long)a.seg_in[cur.b].off + cur.q0 + ka.minoff;
+        }
         for (int kb = 0; kb < ka.NKB; ++kb) {
           const int kcl = (kb == ka.NKB - 1) ? ka.kc_last_load : ka.KC;
           mbar_wait(A_EMPTY(sa), pa ^ 1);
-          mbar_expect_tx(A_FULL(sa), (uint32_t)(kcl * arows * 16));
-          const uint32_t adst = smem_u32(a_smem + (size_t)sa * ka.a_stage_bytes);
-          for (int c = 0; c < kcl; ++c) {
-            const __nv_bfloat16* src = xg + ((size_t)(kb * ka.KC + c) * a.Rx + row0) * 8;
-            bulk_g2s(adst + (uint32_t)(c * ka.astride) * 16, src, (uint32_t)(arows * 16), A_FULL(sa));
+          TRACE(0, 2, t);
+          if (ka.debug & 4) {
+            mbar_arrive(A_FULL(sa));
+          } else {
+            mbar_expect_tx(A_FULL(sa), (uint32_t)(kcl * arows * 16));
+            const uint32_t adst = smem_u32(a_smem + (size_t)sa * ka.a_stage_bytes);
+            for (int c = 0; c < kcl; ++c) {
+              const __nv_bfloat16* src = xg + ((size_t)(kb * ka.KC + c) * a.Rx + row0c) * 8;
+              bulk_g2s(adst + (uint32_t)(c * ka.astride) * 16, src, (uint32_t)(arows * 16), A_FULL(sa));
+            }
           }
           if (++sa == ka.NA) { sa = 0; pa ^= 1; }
           if (!ka.b_resident || first) {
@@ -316,35 +334,37 @@ __global__ void __launch_bounds__(64 + 32 * 8, 1) conv_umma_kernel(const UmmaKer
           }
         }
         first = false;
+        t = tn;
       }
     }
+    __syncwarp();
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    // The WHOLE warp runs the loops so every address / descriptor computation is warp-uniform and the
-    // compiler keeps it in uniform registers (tcgen05.mma takes its descriptors from URs; computing them
-    // in a divergent single-lane region costs an R2UR round trip per operand per MMA -- measured with
-    // tools/umma_bench.cu: ~124 cycles per MMA instead of the N/2-cycle floor).  Only the tcgen05
-    // instructions themselves are predicated on one elected lane.
-    {
+    // ===================== MMA issuer (one thread) =====================
+    // Single-thread region selected with elect.sync: every address / descriptor computation is then
+    // uniform and ptxas keeps it in uniform registers (tcgen05.mma takes its descriptors from URs).
+    if (elect_one()) {
       // instruction descriptor: D=f32, A=B=bf16, both K-major, N=BN, M=128
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(ka.BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       const uint32_t lbo_a = (uint32_t)ka.astride * 16, lbo_b = (uint32_t)ka.BN * 16;
       // Descriptors differ only in the 14-bit start-address field (bits 0-13 of the low word).
       const uint64_t adesc0 = make_desc(0, lbo_a, 128), bdesc0 = make_desc(0, lbo_b, 128);
       const uint32_t a_kstep = (2u * lbo_a) >> 4, b_kstep = (2u * lbo_b) >> 4;
-      const int nk16 = ka.KC / 2;
+      const int nk16 = (ka.debug & 2) ? 0 : ka.KC / 2;
       const uint32_t a_smem_lo = (smem_u32(a_smem) & 0x3FFFFu) >> 4, b_smem_lo = (smem_u32(b_smem) & 0x3FFFFu) >> 4;
       const uint32_t a_stage_lo = (uint32_t)ka.a_stage_bytes >> 4, b_stage_lo = (uint32_t)ka.b_stage_bytes >> 4;
-      const bool two = ka.MSUB == 2;
+      const int msub = ka.MSUB;
       int sa = 0, pa = 0, sb = 0, pb = 0, acc = 0, pacc = 0;
       bool first = true;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        TRACE(1, 0, t);
         mbar_wait(T_EMPTY(acc), pacc ^ 1);   // epilogue has drained this accumulator stage
+        TRACE(1, 1, t);
         tc_fence_after();
-        const uint32_t d0 = tmem_base + (uint32_t)(acc * acc_cols), d1 = d0 + (uint32_t)ka.BNC;
+        const uint32_t d0 = tmem_base + (uint32_t)(acc * acc_cols);
         uint32_t accum = 0;
         for (int kb = 0; kb < ka.NKB; ++kb) {
           mbar_wait(A_FULL(sa), pa);
+          TRACE(1, 2, t);
           tc_fence_after();
           const uint64_t adesc_stage = adesc0 + (a_smem_lo + (uint32_t)sa * a_stage_lo);
           for (int tap = 0; tap < a.ntaps; ++tap) {
@@ -352,129 +372,123 @@ __global__ void __launch_bounds__(64 + 32 * 8, 1) conv_umma_kernel(const UmmaKer
               mbar_wait(B_FULL(sb), pb);
               tc_fence_after();
             }
-            uint64_t adesc = adesc_stage + (uint32_t)(a.tap_off[tap] - ka.minoff);   // row shift of this tap (>= 0)
-            uint64_t bdesc = bdesc0 + (b_smem_lo + (uint32_t)sb * b_stage_lo);
-            // alternate the two accumulators so consecutive MMAs are independent
-            if (elect_one()) {   // single-thread region: descriptors live in uniform registers across the loop
-#pragma unroll 2
-              for (int k16 = 0; k16 < nk16; ++k16) {
-                umma_bf16(d0, adesc, bdesc, idesc, accum | (uint32_t)k16);
-                if (two) umma_bf16(d1, adesc + 128u, bdesc, idesc, accum | (uint32_t)k16);   // +128 rows
-                adesc += a_kstep; bdesc += b_kstep;
-              }
-              if (!ka.b_resident) umma_commit(B_EMPTY(sb));
-            }
-            __syncwarp();
+            const uint64_t adesc = adesc_stage + (uint32_t)(a.tap_off[tap] - ka.minoff);   // row shift of this tap (>= 0)
+            const uint64_t bdesc = bdesc0 + (b_smem_lo + (uint32_t)sb * b_stage_lo);
+            if (msub == 2) issue_tap<2>(d0, (uint32_t)ka.BNC, adesc, bdesc, idesc, accum, nk16, a_kstep, b_kstep);
+            else if (msub == 4) issue_tap<4>(d0, (uint32_t)ka.BNC, adesc, bdesc, idesc, accum, nk16, a_kstep, b_kstep);
+            else issue_tap<1>(d0, (uint32_t)ka.BNC, adesc, bdesc, idesc, accum, nk16, a_kstep, b_kstep);
             accum = 1;
+            if (!ka.b_resident) umma_commit(B_EMPTY(sb));
             if (++sb == ka.NB) { sb = 0; pb ^= 1; }
           }
-          if (elect_one()) umma_commit(A_EMPTY(sa));
+          umma_commit(A_EMPTY(sa));
           if (++sa == ka.NA) { sa = 0; pa ^= 1; }
         }
-        if (elect_one()) umma_commit(T_FULL(acc));
+        umma_commit(T_FULL(acc));
+        TRACE(1, 3, t);
         if (++acc == ka.ACC) { acc = 0; pacc ^= 1; }
         first = false;
-        __syncwarp();
       }
     }
+    __syncwarp();
   } else {
     // ===================== epilogue =====================
-    const int e = warp - 2;
     const int quarter = warp & 3;            // TMEM lanes this warp may touch: 32*quarter ..
-    const int split = e >> 2, nsplit = ka.EPIW >> 2;
-    const int nchunks = ka.BN >> 3;
+    const int half = (warp - 2) >> 2;        // the two warps of a quarter alternate over work items
+    const int ngroups = ka.BNC >> 5;         // 32-column groups per accumulator
+    const int nitems = ka.MSUB * ngroups;
     const int N = a.u * a.Cout;
+    const bool tr = warp == 2 && lane == 0;
+    const bool plain = a.u == 1;
     __nv_bfloat16* yg = reinterpret_cast<__nv_bfloat16*>(a.y);
     const __nv_bfloat16* rg = reinterpret_cast<const __nv_bfloat16*>(a.res);
+    const size_t cs = (size_t)a.Ry * 8;      // elements between consecutive 8-channel chunks
     int acc = 0, pacc = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      int nt, b, q0;
-      decode(t, nt, b, q0);
-      const SegDesc so = a.seg_out[b];
-      const int Lq = a.seg_in[b].len + a.q_extra;
-      const int n0 = nt * ka.BN;
+    int t = blockIdx.x;
+    TileRef cur = t < total_tiles ? decode(t) : TileRef{0, 0, 0};
+    SegDesc so = a.seg_out[cur.b];
+    int Lq = a.seg_in[cur.b].len + a.q_extra;
+    while (t < total_tiles) {
+      if (tr) TRACE(2, 0, t);
+      const TileRef tl = cur;
+      const SegDesc soc = so;
+      const int Lqc = Lq;
+      const int tn = t + gridDim.x;
+      if (tn < total_tiles) {   // prefetch the next tile's coordinates before blocking
+        cur = decode(tn);
+        so = a.seg_out[cur.b];
+        Lq = a.seg_in[cur.b].len + a.q_extra;
+      }
+      const int n0 = tl.nt * ka.BN;
+      const float* biasp = a.bias ? a.bias + (size_t)tl.b * a.bias_bstride : nullptr;
+      if (tr) TRACE(2, 1, t);
       mbar_wait(T_FULL(acc), pacc);
+      if (tr) TRACE(2, 2, t);
       tc_fence_after();
-      for (int sub = 0; sub < ka.MSUB; ++sub) {
-        const int q = q0 + sub * 128 + quarter * 32 + lane;
-        const bool qok = q < Lq;
-        const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * acc_cols + sub * ka.BNC);
-        if (a.u == 1) {
-          // plain convolution: output row == q, column n == channel
-          const bool valid = qok && q < so.len;
-          const size_t base = ((size_t)(n0 >> 3) * a.Ry + so.off + q) * 8, cs = (size_t)a.Ry * 8;
-          const float* bias = a.bias ? a.bias + (size_t)b * a.bias_bstride + n0 : nullptr;
-          int nvalid = (N - n0 + 7) >> 3;
-          nvalid = nvalid < nchunks ? nvalid : nchunks;
-          if (rg) {
-            if (a.accumulate) epilogue_rows<true, true>(trow, yg + base, rg + base, cs, bias, a.out_scale, valid, split, nsplit, nchunks, nvalid);
-            else epilogue_rows<true, false>(trow, yg + base, rg + base, cs, bias, a.out_scale, valid, split, nsplit, nchunks, nvalid);
-          } else {
-            if (a.accumulate) epilogue_rows<false, true>(trow, yg + base, nullptr, cs, bias, a.out_scale, valid, split, nsplit, nchunks, nvalid);
-            else epilogue_rows<false, false>(trow, yg + base, nullptr, cs, bias, a.out_scale, valid, split, nsplit, nchunks, nvalid);
-          }
-          continue;
-        }
-        for (int c0 = split; c0 < nchunks; c0 += 4 * nsplit) {
-          uint32_t r[4][8];
+      for (int item = half; item < nitems; item += 2) {
+        const int sub = item / ngroups, grp = item - sub * ngroups;
+        const int q = tl.q0 + sub * 128 + quarter * 32 + lane;
+        const bool qok = q < Lqc && !(ka.debug & 1);
+        uint32_t r[32];
+        __syncwarp();   // tcgen05.ld is .sync.aligned: reconverge after the predicated stores below
+        tmem_ld32_nowait(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * acc_cols + sub * ka.BNC + grp * 32), r);
+        const int nbase = n0 + grp * 32;     // first GEMM column of this group
+        if (plain) {
+          // plain convolution: output row == q, column == channel; chunk c lives cs elements further
+          const bool valid = qok && q < soc.len;
+          const size_t base = ((size_t)(nbase >> 3) * a.Ry + soc.off + q) * 8;
           uint4 resv[4], oldv[4];
-          size_t off[4];
-          bool ok[4];
-          __syncwarp();   // tcgen05.ld is .sync.aligned: reconverge after the predicated stores below
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            const int c = min(c0 + u * nsplit, nchunks - 1);   // clamped: always a legal column
-            tmem_ld8_nowait(trow + (uint32_t)(c * 8), r[u]);
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int c = c0 + u * nsplit;
-            const int n = n0 + c * 8;
-            ok[u] = false;
-            if (c < nchunks && n < N && qok) {
-              const int phase = n / a.Cout, co = n - phase * a.Cout;
-              const int orow = q * a.u + phase - a.p;
-              if (orow >= 0 && orow < so.len) {
-                ok[u] = true;
-                off[u] = ((size_t)(co >> 3) * a.Ry + so.off + orow) * 8;
-                if (rg) resv[u] = *reinterpret_cast<const uint4*>(rg + off[u]);
-                if (a.accumulate) oldv[u] = *reinterpret_cast<const uint4*>(yg + off[u]);
-              }
+            if (valid && nbase + 8 * u < N) {
+              if (rg) resv[u] = *reinterpret_cast<const uint4*>(rg + base + u * cs);
+              if (a.accumulate) oldv[u] = *reinterpret_cast<const uint4*>(yg + base + u * cs);
             }
           }
           tmem_ld_wait();
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            if (!ok[u]) continue;
-            const int c = c0 + u * nsplit;
-            const int n = n0 + c * 8;
-            const int co = n % a.Cout;
+            if (!(valid && nbase + 8 * u < N)) continue;
             float v[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[u][j]);
-            if (a.bias) {
-              const float4* bp = reinterpret_cast<const float4*>(a.bias + (size_t)b * a.bias_bstride + co);
-              const float4 b0 = bp[0], b1 = bp[1];
+            for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[8 * u + j]);
+            if (biasp) {   // same address for the whole warp: one broadcast L1 transaction
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(biasp + nbase + 8 * u));
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(biasp + nbase + 8 * u + 4));
               v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
               v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
             }
-            if (rg) {
-              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&resv[u]);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) { float2 f = __bfloat1622float2(h[j]); v[2 * j] += f.x; v[2 * j + 1] += f.y; }
-            }
+            if (rg) unpack_add(resv[u], v);
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[j] *= a.out_scale;
-            if (a.accumulate) {
-              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&oldv[u]);
+            if (a.accumulate) unpack_add(oldv[u], v);
+            *reinterpret_cast<uint4*>(yg + base + u * cs) = pack8(v);
+          }
+        } else {
+          // transposed convolution: column n = (phase, channel), output row = q*u + phase - p
+          tmem_ld_wait();
 #pragma unroll
-              for (int j = 0; j < 4; ++j) { float2 f = __bfloat1622float2(h[j]); v[2 * j] += f.x; v[2 * j + 1] += f.y; }
+          for (int u = 0; u < 4; ++u) {
+            const int n = nbase + 8 * u;
+            if (!(qok && n < N)) continue;
+            const int phase = n / a.Cout, co = n - phase * a.Cout;
+            const int orow = q * a.u + phase - a.p;
+            if (orow < 0 || orow >= soc.len) continue;
+            const size_t off = ((size_t)(co >> 3) * a.Ry + soc.off + orow) * 8;
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[8 * u + j]);
+            if (biasp) {
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(biasp + co));
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(biasp + co + 4));
+              v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+              v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
             }
-            uint4 o;
-            __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+            if (rg) { const uint4 p = *reinterpret_cast<const uint4*>(rg + off); unpack_add(p, v); }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) oh[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-            *reinterpret_cast<uint4*>(yg + off[u]) = o;
+            for (int j = 0; j < 8; ++j) v[j] *= a.out_scale;
+            if (a.accumulate) { const uint4 p = *reinterpret_cast<const uint4*>(yg + off); unpack_add(p, v); }
+            *reinterpret_cast<uint4*>(yg + off) = pack8(v);
           }
         }
       }
@@ -482,7 +496,19 @@ __global__ void __launch_bounds__(64 + 32 * 8, 1) conv_umma_kernel(const UmmaKer
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(T_EMPTY(acc));
+      if (tr) TRACE(2, 3, t);
       if (++acc == ka.ACC) { acc = 0; pacc ^= 1; }
+      t = tn;
+    }
+  }
+  if (ka.trace && blockIdx.x == 0 && warp < 3) {
+    __syncwarp();
+    if (tr_n > 0 || lane == 0) {
+      // the tracing lane of each role flushes its ring (only one lane per role has tr_n > 0)
+      if (tr_n > 0) {
+        ka.trace[warp] = (unsigned long long)tr_n;
+        for (int i = 0; i < tr_n; ++i) ka.trace[4 + warp * 1024 + i] = tr_smem[warp * 1024 + i];
+      }
     }
   }
   tc_fence_before();
@@ -517,8 +543,8 @@ void tap_range(const ConvArgs& a, int& mn, int& mx) {
   for (int j = 1; j < a.ntaps; ++j) { mn = a.tap_off[j] < mn ? a.tap_off[j] : mn; mx = a.tap_off[j] > mx ? a.tap_off[j] : mx; }
 }
 
-// Launch-time configuration (depends on the batch geometry as well as on the layer).
-bool configure(const ConvArgs& a, UmmaKernelArgs& ka, size_t& smem_bytes) {
+// Launch-time configuration for a given number of 128-row sub-tiles per tile.
+bool configure(const ConvArgs& a, int msub, UmmaKernelArgs& ka, size_t& smem_bytes) {
   const int N = a.u * a.Cout;
   const UmmaTiling t = make_tiling(a.ntaps, a.Cin, N);
   if (!t.ok) return false;
@@ -528,7 +554,7 @@ bool configure(const ConvArgs& a, UmmaKernelArgs& ka, size_t& smem_bytes) {
   ka.c = a;
   ka.KC = t.KC; ka.NKB = t.NKB; ka.BN = t.BN; ka.BNC = t.BNC; ka.NT = t.NT;
   ka.minoff = mn; ka.span = mx - mn;
-  ka.MSUB = a.msub == 2 ? 2 : 1;
+  ka.MSUB = msub;
   ka.ACC = 512 / (ka.MSUB * ka.BNC);
   if (ka.ACC > 4) ka.ACC = 4;
   if (ka.ACC < 1) return false;
@@ -538,8 +564,9 @@ bool configure(const ConvArgs& a, UmmaKernelArgs& ka, size_t& smem_bytes) {
   ka.a_stage_bytes = t.KC * ka.astride * 16;
   ka.b_stage_bytes = t.KC * t.BN * 16;
   ka.kc_last_load = a.Cin / 8 - (t.NKB - 1) * t.KC;
-  static const int epiw_env = env_int("BVG_CONV_EPIW", 8);
-  ka.EPIW = epiw_env == 4 ? 4 : 8;
+  static const int debug_env = env_int("BVG_CONV_DEBUG", 0);
+  ka.debug = debug_env;
+  ka.trace = nullptr;
   // pipeline depths within the smem budget
   const int total_b = t.NKB * a.ntaps;
   ka.NA = t.NKB > 1 ? 2 : 3;
@@ -552,13 +579,12 @@ bool configure(const ConvArgs& a, UmmaKernelArgs& ka, size_t& smem_bytes) {
     int na = (int)((SMEM_BUDGET - (size_t)total_b * ka.b_stage_bytes) / ka.a_stage_bytes);
     ka.NA = na > 4 ? 4 : na;   // >= 2 by the test above
   } else {
+    if ((size_t)ka.NA * ka.a_stage_bytes + 2 * (size_t)ka.b_stage_bytes > (size_t)SMEM_BUDGET) ka.NA = 2;
+    if ((size_t)ka.NA * ka.a_stage_bytes + 2 * (size_t)ka.b_stage_bytes > (size_t)SMEM_BUDGET) return false;
     int nb = (SMEM_BUDGET - ka.NA * ka.a_stage_bytes) / ka.b_stage_bytes;
     if (nb > 8) nb = 8;
     if (nb > total_b) nb = total_b;
-    if (nb < 2 && total_b >= 2) {
-      if (ka.NA > 2) { ka.NA = 2; nb = (SMEM_BUDGET - ka.NA * ka.a_stage_bytes) / ka.b_stage_bytes; }
-      if (nb < 2) return false;
-    }
+    if (nb < 1) return false;
     ka.NB = nb;
   }
   smem_bytes = (size_t)ka.NA * ka.a_stage_bytes + (size_t)ka.NB * ka.b_stage_bytes +
@@ -584,23 +610,34 @@ cudaError_t launch_repack_umma(const float* wp_tap_major, void* img, int ntaps, 
   return cudaGetLastError();
 }
 
+// Sub-tiles per tile: as many as still leave >= 2 TMEM accumulator stages (epilogue/MMA overlap) and
+// fit the shared-memory budget; small problems keep small tiles so all SMs get work.
 int conv_umma_default_msub(const ConvArgs& a) {
   static const int forced = env_int("BVG_CONV_MSUB", 0);
-  if (forced == 1 || forced == 2) return forced;
-  return a.max_q > 128 ? 2 : 1;
+  const UmmaTiling t = make_tiling(a.ntaps, a.Cin, a.u * a.Cout);
+  if (!t.ok) return 1;
+  for (int msub = 4; msub >= 2; msub >>= 1) {
+    if (forced && msub > forced) continue;
+    if (a.max_q <= 128 * (msub / 2)) continue;
+    if (msub * t.BNC * 2 > 512) continue;
+    UmmaKernelArgs ka{};
+    size_t smem;
+    if (configure(a, msub, ka, smem)) return msub;
+  }
+  return 1;
 }
 
 bool conv_umma_supported(const ConvArgs& a) {
   UmmaKernelArgs ka{};
   size_t smem;
-  return a.tile_prefix != nullptr && configure(a, ka, smem);
+  return a.tile_prefix != nullptr && (a.msub == 1 || a.msub == 2 || a.msub == 4) && configure(a, a.msub, ka, smem);
 }
 
 cudaError_t launch_conv_umma(const ConvArgs& a, cudaStream_t s) {
   if (a.B <= 0 || a.max_q <= 0 || a.total_mt <= 0) return cudaSuccess;
   UmmaKernelArgs ka{};
   size_t smem;
-  if (!configure(a, ka, smem)) return cudaErrorInvalidValue;
+  if (!configure(a, a.msub, ka, smem)) return cudaErrorInvalidValue;
   ka.tile_prefix = a.tile_prefix;
   ka.total_mt = a.total_mt;
   static int num_sms = 0;
@@ -611,8 +648,34 @@ cudaError_t launch_conv_umma(const ConvArgs& a, cudaStream_t s) {
     cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX);
     if (e != cudaSuccess) { num_sms = 0; return e; }
   }
+  static const int trace_cin = env_int("BVG_CONV_TRACE", 0);   // e.g. 24: trace the first k=3 conv with Cin == 24
+  static bool traced = false;
+  const bool do_trace = trace_cin > 0 && !traced && a.Cin == trace_cin && a.u == 1 && a.ntaps == 3;
+  if (do_trace) {
+    cudaMalloc((void**)&ka.trace, (4 + 3 * 1024) * 8);
+    cudaMemset(ka.trace, 0, (4 + 3 * 1024) * 8);
+    traced = true;
+    smem = SMEM_MAX;
+  }
   const int total_tiles = ka.total_mt * ka.NT;
-  dim3 grid(total_tiles < num_sms ? total_tiles : num_sms), block(64 + 32 * ka.EPIW);
+  dim3 grid(total_tiles < num_sms ? total_tiles : num_sms), block(NTHREADS);
   conv_umma_kernel<<<grid, block, smem, s>>>(ka);
+  if (do_trace) {
+    cudaStreamSynchronize(s);
+    static unsigned long long h[4 + 3 * 1024];
+    cudaMemcpy(h, ka.trace, sizeof h, cudaMemcpyDeviceToHost);
+    FILE* f = fopen("gpurun_out/conv_trace.txt", "w");
+    if (f) {
+      fprintf(f, "# NA %d NB %d ACC %d MSUB %d BN %d KC %d NKB %d resident %d tiles %d grid %d\n", ka.NA, ka.NB, ka.ACC,
+              ka.MSUB, ka.BN, ka.KC, ka.NKB, ka.b_resident, total_tiles, (int)grid.x);
+      for (int role = 0; role < 3; ++role)
+        for (unsigned long long i = 0; i < h[role] && i < 1024; ++i) {
+          unsigned long long v = h[4 + role * 1024 + i];
+          fprintf(f, "%d %llu %llu %llu\n", role, v >> 56, (v >> 40) & 0xffff, v & 0xffffffffffULL);
+        }
+      fclose(f);
+    }
+    cudaFree(ka.trace);
+  }
   return cudaGetLastError();
 }

@@ -152,6 +152,26 @@ def test_cfg2_bf16_vs_fp32_mode(gen):
     assert snr >= BF16_SNR_DB
 
 
+def test_cfg3_srt_workload_batched_equals_single(gen):
+    """Config 3 of BASELINE.json: 512 variable-length SRT segments (1-15 s), decoded in length-bucketed
+    ragged batches (the per-GPU part of the sharded dubbing job).  Spot-checked segments must equal
+    their stand-alone decode bit for bit; every waveform must be finite and of the right length."""
+    from b200vgan import sched, synth
+    frames = sched.srt_workload()                       # 512 segments, ~4096 s of audio
+    rng = np.random.default_rng(3)
+    lat = [torch.from_numpy(rng.standard_normal((f, 1024), dtype=np.float32)).cuda() for f in frames]
+    emb = torch.from_numpy(synth.make_speaker_embedding(B=1)).cuda()
+    gen.precision = "bf16"
+    mine = sched.lpt_shards(frames, 8)[3]               # the shard rank 3 of 8 would own
+    out = sched.decode_segments(gen, lat, emb, indices=mine, max_batch_frames=4096, max_batch=32)
+    assert sorted(out.keys()) == sorted(mine)
+    for i in mine:
+        assert out[i].shape[0] == frames[i] * 1024 and bool(torch.isfinite(out[i]).all())
+    for i in (mine[0], mine[len(mine) // 2], mine[-1]):
+        single = gen.forward_with_embedding(lat[i][None], emb)[0, 0].cpu()
+        assert torch.equal(out[i], single)
+
+
 def test_checkpoint_layout_gives_same_audio(gen, synth_sd):
     from b200vgan import synth
     from b200vgan.model import BigVGAN
