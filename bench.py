@@ -220,12 +220,12 @@ def run_ours(args):
             "bound": "tensor", "kernel": "conv_umma_kernel (tcgen05 implicit-GEMM conv1d)" if tc else "conv_simt_kernel",
             "achieved": conv_tflops, "peak": peak_tf, "unit": "TFLOP/s", "frac": conv_tflops / peak_tf,
             "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({pk['src']})",
-            "traffic": None,
+            "traffic": None,   # per-launch DRAM bytes from ncu --set full are in profiles/ (captured per launch, not averaged)
             "launches_per_step": conv["launches"] / args.steps, "ms_per_step": conv["ms"] / args.steps,
             "share_of_step": conv["ms"] / args.steps / step_ms_prof if step_ms_prof else None,
         }
         roofline_act = {
-            "bound": "hbm", "kernel": "act1d_kernel (fused Activation1d)", "achieved": act_gbs, "peak": pk["hbm_gbs"],
+            "bound": "hbm", "kernel": "act1d_c8_v3_kernel (fused Activation1d: up-FIR -> SnakeBeta -> down-FIR)", "achieved": act_gbs, "peak": pk["hbm_gbs"],
             "unit": "GB/s", "frac": act_gbs / pk["hbm_gbs"], "traffic": None,
             "launches_per_step": act["launches"] / args.steps, "ms_per_step": act["ms"] / args.steps,
             "share_of_step": act["ms"] / args.steps / step_ms_prof if step_ms_prof else None,
