@@ -160,6 +160,15 @@ int bvg_conv1d(const float* x, const float* w, const float* bias, const float* r
                int32_t B, int32_t Cin, int32_t Cout, int32_t T, int32_t k, int32_t dilation,
                int32_t mode, void* stream);
 
+/* Activation1d followed by Conv1d (one half-step of AMPBlock1.forward, models.py:69-72): y = conv(act(x)) [+ residual].
+ * *fused (in/out, may be NULL): in = non-zero requests the experimental kernel that computes the activation
+ * inside the tcgen05 convolution's producer stage (BVG_MODE_BF16, layer must fit one CTA tile, Cout <= 256;
+ * bvg_forward uses it only with BVG_FUSE_ACT=1); out = whether that kernel ran.  Otherwise the activation
+ * runs as its own pass, as in bvg_forward.  Same shapes as bvg_conv1d; log_alpha/beta [Cin]. */
+int bvg_act_conv1d(const float* x, const float* log_alpha, const float* log_beta, const float* w, const float* bias,
+                   const float* residual, float* y, int32_t B, int32_t Cin, int32_t Cout, int32_t T, int32_t k,
+                   int32_t dilation, int32_t mode, int32_t* fused, void* stream);
+
 /* ConvTranspose1d with stride u, kernel k, padding (k-u)/2 (models.py:155-161).
  * x [B,Cin,T] fp32, w [Cin,Cout,k] fp32, y [B,Cout,T*u] fp32. */
 int bvg_conv_transpose1d(const float* x, const float* w, const float* bias, float* y, int32_t B,

@@ -20,7 +20,7 @@ SYMBOLS = [
     "bvg_finalize", "bvg_plan_create", "bvg_plan_destroy", "bvg_plan_workspace_bytes", "bvg_plan_max_frames",
     "bvg_plan_num_launches", "bvg_forward", "bvg_forward_host", "bvg_activation1d", "bvg_conv1d",
     "bvg_conv_transpose1d", "bvg_workspace_reset", "bvg_profile_enable", "bvg_profile_read",
-    "bvg_activation1d_packed",
+    "bvg_activation1d_packed", "bvg_act_conv1d",
 ]
 
 
@@ -80,6 +80,7 @@ def load(rebuild: bool = False) -> C.CDLL:
     lib.bvg_activation1d.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp]
     lib.bvg_activation1d_packed.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp]
     lib.bvg_conv1d.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp]
+    lib.bvg_act_conv1d.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp]
     lib.bvg_conv_transpose1d.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp]
     _lib = lib
     return lib

@@ -101,6 +101,7 @@ struct bvg_handle {
   std::vector<void*> owned;
   std::map<const void*, uint64_t> ws_owner;   // workspace -> uid of the plan whose guard rows it holds
   bool finalized = false;
+  int launch_counter = 0;   // kernel launches issued by the forward in progress
   // optional per-launch CUDA-event timing (bench.py's roofline numbers)
   bool prof_on = false;
   std::vector<ProfRec> prof;
@@ -175,7 +176,7 @@ void add_conv_params(bvg_handle* h, const std::string& name, ConvLayer& L) {
 
 ConvArgs make_conv_args(const ConvLayer& L, const bvg_plan* p, int gin, int gout, const void* x, void* y,
                         const void* res, const float* bias, int bias_bstride, float scale, int accumulate,
-                        bool umma) {
+                        bool umma, const ActLayer* act = nullptr) {
   ConvArgs a{};
   a.x = x; a.y = y; a.res = res;
   a.w = umma ? (const void*)L.w_umma : (const void*)L.w_tap;
@@ -188,7 +189,13 @@ ConvArgs make_conv_args(const ConvLayer& L, const bvg_plan* p, int gin, int gout
   a.u = L.u; a.p = L.p; a.q_extra = L.q_extra;
   a.B = p->B; a.max_q = p->maxlen[gin] + L.q_extra;
   a.out_scale = scale; a.accumulate = accumulate;
-  a.msub = conv_umma_default_msub(a);
+  a.msub = 0;
+  if (act && umma) {   // try the fused Activation1d -> conv kernel
+    a.act_alpha = act->alpha; a.act_inv_beta = act->inv_beta;
+    a.msub = conv_umma_fused_msub(a);
+    if (!a.msub) { a.act_alpha = nullptr; a.act_inv_beta = nullptr; }
+  }
+  if (!a.msub) a.msub = conv_umma_default_msub(a);
   const int ti = (gin * 3 + (a.msub == 4 ? 2 : a.msub - 1)) * 2 + (L.q_extra ? 1 : 0);
   a.tile_prefix = p->prefix_dev + (size_t)ti * (p->B + 1);
   a.total_mt = p->total_mt[ti];
@@ -205,13 +212,37 @@ int run_conv(const ConvLayer& L, const bvg_plan* p, int gin, int gout, const voi
     if (conv_umma_supported(a)) {
       ProfScope ps(p->h, s, PROF_CONV_TC, flops, bytes);
       CK(launch_conv_umma(a, s));
+      ++p->h->launch_counter;
       return 0;
     }
   }
   ConvArgs a = make_conv_args(L, p, gin, gout, x, y, res, bias, bias_bstride, scale, accumulate, false);
   ProfScope ps(p->h, s, PROF_CONV_CC, flops, bytes);
   CK(launch_conv_simt(a, p->dtype, s));
+  ++p->h->launch_counter;
   return 0;
+}
+
+int run_act(const ActLayer& A, const bvg_plan* p, int g, const void* x, void* y, cudaStream_t s);
+
+// Activation1d followed by a convolution (one step of AMPBlock1.forward, models.py:69-72).  In the bf16
+// mode the activation is fused into the conv kernel's producer stage when the layer allows it (the whole
+// N fits one CTA tile); otherwise it runs as its own pass through `actbuf`.
+int run_act_conv(const ActLayer& A, const ConvLayer& L, const bvg_plan* p, int g, const void* raw, void* actbuf,
+                 void* y, const void* res, float scale, int accumulate, cudaStream_t s) {
+  if (p->mode == BVG_MODE_BF16 && L.w_umma) {
+    ConvArgs a = make_conv_args(L, p, g, g, raw, y, res, L.bias, 0, scale, accumulate, true, &A);
+    if (a.act_alpha && conv_umma_supported(a)) {
+      const double flops = 2.0 * L.Cin * L.ntaps * L.N * (double)p->sumlen[g];
+      const double bytes = ((double)L.Cin * p->sumlen[g] + (double)L.Cout * p->sumlen[g] * (res ? 2 : 1)) * p->esize;
+      ProfScope ps(p->h, s, PROF_CONV_TC, flops, bytes);
+      CK(launch_conv_umma(a, s));
+      ++p->h->launch_counter;
+      return 0;
+    }
+  }
+  if (run_act(A, p, g, raw, actbuf, s)) return 1;
+  return run_conv(L, p, g, g, actbuf, y, res, L.bias, 0, scale, accumulate, s);
 }
 
 int run_act(const ActLayer& A, const bvg_plan* p, int g, const void* x, void* y, cudaStream_t s) {
@@ -220,6 +251,7 @@ int run_act(const ActLayer& A, const bvg_plan* p, int g, const void* x, void* y,
   const double bytes = 2.0 * p->C[g] * (double)p->sumlen[g] * p->esize;
   ProfScope ps(p->h, s, PROF_ACT, 0.0, bytes);
   CK(launch_act_c8(aa, p->dtype, p->mode == BVG_MODE_FP32, s));
+  ++p->h->launch_counter;
   return 0;
 }
 
@@ -518,6 +550,7 @@ int bvg_forward(bvg_handle* h, bvg_plan* p, const void* latent, int32_t latent_d
     }
   }
   const SegDesc* seg0 = p->seg_dev;
+  h->launch_counter = 1 + ng + 1;   // pack + cond biases + conv_post (the helpers below count their own)
   float* biasb = (float*)(ws + p->off_bias);
   const int D = h->cfg.speaker_embedding_dim;
   {
@@ -549,13 +582,11 @@ int bvg_forward(bvg_handle* h, bvg_plan* p, const void* latent, int32_t latent_d
         const char* xin = m == 0 ? U : X;
         const ActLayer& a1 = h->acts[(size_t)rb * 2 * h->nd + 2 * m];
         const ActLayer& a2 = h->acts[(size_t)rb * 2 * h->nd + 2 * m + 1];
-        if (run_act(a1, p, g, xin, A, s)) return 1;
         const ConvLayer& c1 = h->c1[(size_t)rb * h->nd + m];
-        if (run_conv(c1, p, g, g, A, Y, nullptr, c1.bias, 0, 1.f, 0, s)) return 1;
-        if (run_act(a2, p, g, Y, A, s)) return 1;
+        if (run_act_conv(a1, c1, p, g, xin, A, Y, nullptr, 1.f, 0, s)) return 1;
         const ConvLayer& c2 = h->c2[(size_t)rb * h->nd + m];
         const bool last = m == h->nd - 1;
-        if (run_conv(c2, p, g, g, A, last ? XS : X, xin, c2.bias, 0, last ? 1.f / h->nk : 1.f, last && j > 0, s))
+        if (run_act_conv(a2, c2, p, g, Y, A, last ? XS : X, xin, last ? 1.f / h->nk : 1.f, last && j > 0, s))
           return 1;
       }
     }
@@ -570,6 +601,7 @@ int bvg_forward(bvg_handle* h, bvg_plan* p, const void* latent, int32_t latent_d
     CK(launch_conv_post_tanh(ws + p->off_A[g], dt, h->conv_post.w_raw, h->conv_post.bias, wav, seg, B, p->C[g], p->R[g],
                              p->max_frames * h->hop, s));
   }
+  p->num_launches = h->launch_counter;   // what this forward actually issued (fused layers launch once)
   return 0;
 }
 
@@ -650,7 +682,8 @@ struct OpTemps {
 };
 
 int conv_op(bool transposed, const float* x, const float* w, const float* bias, const float* residual, float* y,
-            int B, int Cin, int Cout, int T, int k, int d, int u, int mode, cudaStream_t s) {
+            int B, int Cin, int Cout, int T, int k, int d, int u, int mode, cudaStream_t s,
+            const float* log_alpha = nullptr, const float* log_beta = nullptr, int* fused_out = nullptr) {
   if (bvg_device_check()) return 1;
   if (!x || !w || !y) return fail("conv op: null argument");
   if (Cin % 8 || Cout % 8) return fail("conv op: Cin and Cout must be multiples of 8");
@@ -693,8 +726,26 @@ int conv_op(bool transposed, const float* x, const float* w, const float* bias, 
   a.u = L.u; a.p = L.p; a.q_extra = L.q_extra; a.B = B; a.max_q = T + L.q_extra;
   a.out_scale = 1.f; a.accumulate = 0;
   a.tile_prefix = nullptr; a.total_mt = 0; a.msub = 1;
+  if (log_alpha && log_beta) {   // Activation1d in front of the convolution
+    float* prm;
+    if (tmp.alloc((void**)&prm, 2 * (size_t)Cin * sizeof(float))) return 1;
+    CK(launch_snake_params(log_alpha, log_beta, prm, prm + Cin, Cin, s));
+    a.act_alpha = prm; a.act_inv_beta = prm + Cin;
+    const int fm = mode == BVG_MODE_BF16 ? conv_umma_fused_msub(a, fused_out && *fused_out) : 0;
+    if (fused_out) *fused_out = fm ? 1 : 0;
+    if (fm) {
+      a.msub = fm;
+    } else {         // separate pass, as bvg_forward does for layers the fused kernel does not cover
+      void* ac;
+      if (tmp.alloc(&ac, (size_t)Cin * Rin * es)) return 1;
+      CK(cudaMemsetAsync(ac, 0, (size_t)Cin * Rin * es, s));
+      ActArgs aa{xc, ac, prm, prm + Cin, seg_dev, Rin, Cin, B, T};
+      CK(launch_act_c8(aa, dt, mode == BVG_MODE_FP32, s));
+      a.x = ac; a.act_alpha = nullptr; a.act_inv_beta = nullptr;
+    }
+  }
   if (mode == BVG_MODE_BF16) {
-    a.msub = conv_umma_default_msub(a);
+    if (!a.act_alpha) a.msub = conv_umma_default_msub(a);
     std::vector<int> pf(B + 1, 0);
     for (int b = 0; b < B; ++b) pf[b + 1] = pf[b] + (T + L.q_extra + 128 * a.msub - 1) / (128 * a.msub);
     int* pf_dev;
@@ -748,6 +799,17 @@ int bvg_activation1d_packed(const float* x, float* y, const float* log_alpha, co
 int bvg_conv1d(const float* x, const float* w, const float* bias, const float* residual, float* y, int32_t B,
                int32_t Cin, int32_t Cout, int32_t T, int32_t k, int32_t dilation, int32_t mode, void* stream) {
   return conv_op(false, x, w, bias, residual, y, B, Cin, Cout, T, k, dilation, 1, mode, (cudaStream_t)stream);
+}
+
+int bvg_act_conv1d(const float* x, const float* log_alpha, const float* log_beta, const float* w, const float* bias,
+                   const float* residual, float* y, int32_t B, int32_t Cin, int32_t Cout, int32_t T, int32_t k,
+                   int32_t dilation, int32_t mode, int32_t* fused, void* stream) {
+  if (!log_alpha || !log_beta) return fail("bvg_act_conv1d: null activation parameters");
+  int f = fused ? *fused : 0;   // in: request the fused kernel even if BVG_FUSE_ACT is off
+  int rc = conv_op(false, x, w, bias, residual, y, B, Cin, Cout, T, k, dilation, 1, mode, (cudaStream_t)stream, log_alpha,
+                   log_beta, &f);
+  if (fused) *fused = f;
+  return rc;
 }
 
 int bvg_conv_transpose1d(const float* x, const float* w, const float* bias, float* y, int32_t B, int32_t Cin,

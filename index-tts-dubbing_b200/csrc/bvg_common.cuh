@@ -50,6 +50,10 @@ struct ConvArgs {
   const int* tile_prefix;   // [B+1] prefix sum of tiles per segment (device)
   int total_mt;             // tile_prefix[B]
   int msub;                 // 1, 2 or 4
+  // fused Activation1d (tcgen05 kernel, bf16): when set, x is the RAW input and the kernel applies the
+  // activation with these per-input-channel parameters while staging its A operand
+  const float* act_alpha;
+  const float* act_inv_beta;
 };
 
 struct ActArgs {
@@ -117,3 +121,4 @@ cudaError_t launch_conv_simt(const ConvArgs& a, int dtype, cudaStream_t s);
 cudaError_t launch_conv_umma(const ConvArgs& a, cudaStream_t s);
 bool conv_umma_supported(const ConvArgs& a);
 int conv_umma_default_msub(const ConvArgs& a);
+int conv_umma_fused_msub(const ConvArgs& a, bool force = false);   // 0 = this conv cannot take the fused activation

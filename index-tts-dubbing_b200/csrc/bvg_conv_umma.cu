@@ -33,7 +33,9 @@
 //     latency), not by MMA or HBM -> big tiles (MSUB = 4), x32 TMEM loads, decode prefetch.
 #include <cstdio>
 #include <cstdlib>
+#include <type_traits>
 
+#include "bvg_act_core.cuh"
 #include "bvg_common.cuh"
 #include "bvg_misc.cuh"
 
@@ -43,8 +45,14 @@ constexpr int MAXSPAN = 50;
 constexpr int SMEM_BUDGET = 200 * 1024;   // operand stages; barriers etc. come on top
 constexpr int SMEM_MAX = 224 * 1024;
 constexpr int MAX_STAGES = 12;
+constexpr int SBIAS_MAX = 512;             // columns of batch-independent bias kept in shared memory
 constexpr int EPIW = 8;                   // epilogue warps
 constexpr int NTHREADS = 64 + 32 * EPIW;
+// fused mode (Activation1d computed in the conv's producer stage): 4 epilogue warps + 10 activation warps
+constexpr int EPIW_FUSED = 4;
+constexpr int NACT = 10;
+constexpr int NTHREADS_FUSED = 64 + 32 * (EPIW_FUSED + NACT);
+constexpr int ACT_RT = 25;                // rows per activation thread (odd: conflict-free 4-byte columns)
 
 struct UmmaTiling {
   int KC, NKB;      // 8-channel chunks per k-block, k-blocks
@@ -215,22 +223,36 @@ struct UmmaKernelArgs {
   int a_stage_bytes, b_stage_bytes;
   int kc_last_load;         // real (non-padding) chunks of the last k-block
   int minoff, span;
+  // fused Activation1d (FUSE kernel only): the producer loads RAW rows into R stages, activation warps
+  // write the activated tile into the A stages
+  const float* act_alpha;   // exp(log_alpha) per input channel
+  const float* act_inv_beta;
+  int NR;                   // raw stages
+  int rstride, r_stage_bytes;
+  int nblk;                 // ACT_RT-row blocks per chunk
+  // residual folded into the accumulator: after the conv k-blocks, NKB more k-blocks take the residual
+  // tile as A operand against identity weight images (appended to the layer's image), so the epilogue
+  // issues no global loads (narrow stages were bound by that latency chain)
+  int res_mma;
   unsigned long long* trace;   // optional event trace of CTA 0 (BVG_CONV_TRACE), nullptr normally
   int debug;                // tuning aid (BVG_CONV_DEBUG): 1 = epilogue skips global memory, 2 = no MMAs, 4 = no A loads
 };
 
 struct TileRef { int nt, b, q0; };
 
-__global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UmmaKernelArgs ka) {
+template <bool FUSE>
+__global__ void __launch_bounds__(FUSE ? NTHREADS_FUSED : NTHREADS, 1) conv_umma_kernel(const UmmaKernelArgs ka) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const ConvArgs& a = ka.c;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = ka.total_mt * ka.NT;
   const int TM = 128 * ka.MSUB;
 
-  // smem carve-up: [A stages][B stages][barriers][tmem slot]
-  uint8_t* a_smem = smem;
-  uint8_t* b_smem = smem + (size_t)ka.NA * ka.a_stage_bytes;
+  // smem carve-up: [R stages (fused only)][A stages][B stages][barriers][tmem slot]
+  uint8_t* r_smem = smem;
+  uint8_t* a_smem = smem + (FUSE ? (size_t)ka.NR * ka.r_stage_bytes : 0);
+  constexpr int epiw = FUSE ? EPIW_FUSED : EPIW;
+  uint8_t* b_smem = a_smem + (size_t)ka.NA * ka.a_stage_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(b_smem + (size_t)ka.NB * ka.b_stage_bytes);
   const uint32_t bar0 = smem_u32(bars);
   auto A_FULL = [&](int s) { return bar0 + 8u * s; };
@@ -239,7 +261,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UmmaKernel
   auto B_EMPTY = [&](int s) { return bar0 + 8u * (2 * ka.NA + ka.NB + s); };
   auto T_FULL = [&](int s) { return bar0 + 8u * (2 * ka.NA + 2 * ka.NB + s); };
   auto T_EMPTY = [&](int s) { return bar0 + 8u * (2 * ka.NA + 2 * ka.NB + ka.ACC + s); };
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * ka.NA + 2 * ka.NB + 2 * ka.ACC);
+  auto R_FULL = [&](int s) { return bar0 + 8u * (2 * ka.NA + 2 * ka.NB + 2 * ka.ACC + s); };
+  auto R_EMPTY = [&](int s) { return bar0 + 8u * (2 * ka.NA + 2 * ka.NB + 2 * ka.ACC + ka.NR + s); };
+  // fused mode: TMA-filled (residual) uses of an A stage complete on their own barrier, because A_FULL
+  // counts the activation warps' arrivals there
+  auto AR_FULL = [&](int s) { return FUSE ? bar0 + 8u * (2 * ka.NA + 2 * ka.NB + 2 * ka.ACC + 2 * ka.NR + s) : A_FULL(s); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * ka.NA + 2 * ka.NB + 2 * ka.ACC + 2 * ka.NR + (FUSE ? ka.NA : 0));
 
   // padding chunks (Cin not a multiple of 16) must read as zero: clear the A stages once
   if (ka.kc_last_load < ka.KC) {
@@ -249,10 +276,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UmmaKernel
     for (int i = threadIdx.x; i < n16; i += blockDim.x) p[i] = z;
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
+  // batch-independent bias (the AMP-block convolutions): staged once in shared memory, zero padded to
+  // whole 32-column groups, so the epilogue reads it with broadcast LDS instead of dependent L1 loads
+  float* sbias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 20) + 15) & ~(uintptr_t)15);
+  const bool use_sbias = a.bias != nullptr && a.bias_bstride == 0 && ka.NT * ka.BN <= SBIAS_MAX;
+  if (use_sbias) {
+    const int N_ = a.u * a.Cout;
+    for (int i = threadIdx.x; i < SBIAS_MAX; i += blockDim.x) sbias[i] = i < N_ ? a.bias[i] : 0.f;
+  }
   if (threadIdx.x == 0) {
-    for (int s = 0; s < ka.NA; ++s) { mbar_init(A_FULL(s), 1); mbar_init(A_EMPTY(s), 1); }
+    for (int s = 0; s < ka.NA; ++s) { mbar_init(A_FULL(s), FUSE ? (uint32_t)NACT : 1u); mbar_init(A_EMPTY(s), 1); }
+    if (FUSE) {
+      for (int s = 0; s < ka.NR; ++s) { mbar_init(R_FULL(s), 1); mbar_init(R_EMPTY(s), (uint32_t)NACT); }
+      for (int s = 0; s < ka.NA; ++s) mbar_init(AR_FULL(s), 1);
+    }
     for (int s = 0; s < ka.NB; ++s) { mbar_init(B_FULL(s), 1); mbar_init(B_EMPTY(s), 1); }
-    for (int s = 0; s < ka.ACC; ++s) { mbar_init(T_FULL(s), 1); mbar_init(T_EMPTY(s), (uint32_t)EPIW); }
+    for (int s = 0; s < ka.ACC; ++s) { mbar_init(T_FULL(s), 1); mbar_init(T_EMPTY(s), (uint32_t)epiw); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), (uint32_t)ka.tmem_cols);
@@ -262,7 +301,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UmmaKernel
   const uint32_t tmem_base = *tmem_slot;
 
   // low-overhead event trace (CTA 0 only): per-role ring in shared memory, flushed at kernel end
-  unsigned long long* tr_smem = reinterpret_cast<unsigned long long*>(smem + (SMEM_MAX - 3 * 1024 * 8));
+  unsigned long long* tr_smem = reinterpret_cast<unsigned long long*>(smem + (SMEM_MAX - 4 * 1024 * 8));
   int tr_n = 0;
   auto TRACE = [&](int role, int ev, int tile) {
     if (ka.trace && blockIdx.x == 0 && tr_n < 1024) {
@@ -294,22 +333,39 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UmmaKernel
     if (elect_one()) {
       const __nv_bfloat16* xg = reinterpret_cast<const __nv_bfloat16*>(a.x);
       const uint8_t* wimg = reinterpret_cast<const uint8_t*>(a.w);
-      int sa = 0, pa = 0, sb = 0, pb = 0;
+      int sa = 0, pa = 0, sb = 0, pb = 0, sr = 0, pr = 0;
       bool first = true;
       int t = blockIdx.x;
       TileRef cur = t < total_tiles ? decode(t) : TileRef{0, 0, 0};
+      const __nv_bfloat16* resg = reinterpret_cast<const __nv_bfloat16*>(a.res);
       long long row0 = t < total_tiles ? (long long)a.seg_in[cur.b].off + cur.q0 + ka.minoff : 0;
+      long long rrow0 = t < total_tiles ? (long long)a.seg_out[cur.b].off + cur.q0 : 0;
       while (t < total_tiles) {
         TRACE(0, 0, t);
         const int tn = t + gridDim.x;
         const int nt = cur.nt;
-        const long long row0c = row0;
+        const long long row0c = row0, rrow0c = rrow0;
         if (tn < total_tiles) {   // prefetch the next tile's coordinates
           cur = decode(tn);
           row0 = (long long)a.seg_in[cur.b].off + cur.q0 + ka.minoff;
+          rrow0 = (long long)a.seg_out[cur.b].off + cur.q0;
         }
         for (int kb = 0; kb < ka.NKB; ++kb) {
           const int kcl = (kb == ka.NKB - 1) ? ka.kc_last_load : ka.KC;
+          if constexpr (FUSE) {
+            // raw rows [row0 - 5, row0 + nblk*ACT_RT + 5) of every chunk: the activation warps consume them
+            const int rrows = ka.nblk * ACT_RT + 10;
+            mbar_wait(R_EMPTY(sr), pr ^ 1);
+            TRACE(0, 2, t);
+            mbar_expect_tx(R_FULL(sr), (uint32_t)(kcl * rrows * 16));
+            const uint32_t rdst = smem_u32(r_smem + (size_t)sr * ka.r_stage_bytes);
+            for (int c = 0; c < kcl; ++c) {
+              const __nv_bfloat16* src = xg + ((size_t)(kb * ka.KC + c) * a.Rx + row0c - 5) * 8;
+              bulk_g2s(rdst + (uint32_t)(c * ka.rstride) * 16, src, (uint32_t)(rrows * 16), R_FULL(sr));
+            }
+            if (++sr == ka.NR) { sr = 0; pr ^= 1; }
+            if (++sa == ka.NA) { sa = 0; pa ^= 1; }   // the activation warps fill this A stage
+          } else {
           mbar_wait(A_EMPTY(sa), pa ^ 1);
           TRACE(0, 2, t);
           if (ka.debug & 4) {
@@ -323,11 +379,33 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UmmaKernel
             }
           }
           if (++sa == ka.NA) { sa = 0; pa ^= 1; }
+          }
           if (!ka.b_resident || first) {
             for (int tap = 0; tap < a.ntaps; ++tap) {
               if (!ka.b_resident) mbar_wait(B_EMPTY(sb), pb ^ 1);
               mbar_expect_tx(B_FULL(sb), (uint32_t)ka.b_stage_bytes);
               const uint8_t* src = wimg + ((size_t)(nt * ka.NKB + kb) * a.ntaps + tap) * ka.b_stage_bytes;
+              bulk_g2s(smem_u32(b_smem + (size_t)sb * ka.b_stage_bytes), src, (uint32_t)ka.b_stage_bytes, B_FULL(sb));
+              if (++sb == ka.NB) { sb = 0; pb ^= 1; }
+            }
+          }
+        }
+        if (ka.res_mma) {
+          // residual k-blocks: the tile's TM output rows of `res`, placed at slab row -minoff
+          for (int kb = 0; kb < ka.NKB; ++kb) {
+            const int kcl = (kb == ka.NKB - 1) ? ka.kc_last_load : ka.KC;
+            mbar_wait(A_EMPTY(sa), pa ^ 1);
+            mbar_expect_tx(AR_FULL(sa), (uint32_t)(kcl * TM * 16));
+            const uint32_t adst = smem_u32(a_smem + (size_t)sa * ka.a_stage_bytes) - (uint32_t)(ka.minoff * 16);
+            for (int c = 0; c < kcl; ++c) {
+              const __nv_bfloat16* src = resg + ((size_t)(kb * ka.KC + c) * a.Ry + rrow0c) * 8;
+              bulk_g2s(adst + (uint32_t)(c * ka.astride) * 16, src, (uint32_t)(TM * 16), AR_FULL(sa));
+            }
+            if (++sa == ka.NA) { sa = 0; pa ^= 1; }
+            if (!ka.b_resident || first) {
+              if (!ka.b_resident) mbar_wait(B_EMPTY(sb), pb ^ 1);
+              mbar_expect_tx(B_FULL(sb), (uint32_t)ka.b_stage_bytes);
+              const uint8_t* src = wimg + ((size_t)ka.NKB * a.ntaps + kb) * ka.b_stage_bytes;   // identity images (NT == 1)
               bulk_g2s(smem_u32(b_smem + (size_t)sb * ka.b_stage_bytes), src, (uint32_t)ka.b_stage_bytes, B_FULL(sb));
               if (++sb == ka.NB) { sb = 0; pb ^= 1; }
             }
@@ -342,66 +420,108 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UmmaKernel
     // ===================== MMA issuer (one thread) =====================
     // Single-thread region selected with elect.sync: every address / descriptor computation is then
     // uniform and ptxas keeps it in uniform registers (tcgen05.mma takes its descriptors from URs).
+    // The tensor pipe queues only a couple of MMAs, so every cycle this thread spends between two taps
+    // is a cycle the pipe idles (measured: ~400 cycles per tap with a naive loop, r1 traces): the tap
+    // loop is kept to a handful of instructions -- 32-bit descriptor words advanced incrementally, the
+    // per-tap row shifts read from a small shared-memory table one tap ahead, MSUB a compile-time constant.
     if (elect_one()) {
-      // instruction descriptor: D=f32, A=B=bf16, both K-major, N=BN, M=128
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(ka.BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-      const uint32_t lbo_a = (uint32_t)ka.astride * 16, lbo_b = (uint32_t)ka.BN * 16;
-      // Descriptors differ only in the 14-bit start-address field (bits 0-13 of the low word).
-      const uint64_t adesc0 = make_desc(0, lbo_a, 128), bdesc0 = make_desc(0, lbo_b, 128);
-      const uint32_t a_kstep = (2u * lbo_a) >> 4, b_kstep = (2u * lbo_b) >> 4;
-      const int nk16 = (ka.debug & 2) ? 0 : ka.KC / 2;
-      const uint32_t a_smem_lo = (smem_u32(a_smem) & 0x3FFFFu) >> 4, b_smem_lo = (smem_u32(b_smem) & 0x3FFFFu) >> 4;
-      const uint32_t a_stage_lo = (uint32_t)ka.a_stage_bytes >> 4, b_stage_lo = (uint32_t)ka.b_stage_bytes >> 4;
-      const int msub = ka.MSUB;
-      int sa = 0, pa = 0, sb = 0, pb = 0, acc = 0, pacc = 0;
-      bool first = true;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        TRACE(1, 0, t);
-        mbar_wait(T_EMPTY(acc), pacc ^ 1);   // epilogue has drained this accumulator stage
-        TRACE(1, 1, t);
-        tc_fence_after();
-        const uint32_t d0 = tmem_base + (uint32_t)(acc * acc_cols);
-        uint32_t accum = 0;
-        for (int kb = 0; kb < ka.NKB; ++kb) {
-          mbar_wait(A_FULL(sa), pa);
-          TRACE(1, 2, t);
+      uint32_t* tapshift = reinterpret_cast<uint32_t*>(tmem_slot + 2);   // [ntaps + 1] row shifts (16-byte units)
+      for (int tp = 0; tp < a.ntaps; ++tp) tapshift[tp] = (uint32_t)(a.tap_off[tp] - ka.minoff);
+      tapshift[a.ntaps] = 0;
+      auto run = [&](auto ms_tag) {
+        constexpr int MS = decltype(ms_tag)::value;
+        // instruction descriptor: D=f32, A=B=bf16, both K-major, N=BN, M=128
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(ka.BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t lbo_a = (uint32_t)ka.astride * 16, lbo_b = (uint32_t)ka.BN * 16;
+        // Descriptors differ only in the 14-bit start-address field (bits 0-13 of the low word).
+        const uint64_t adesc0 = make_desc(0, lbo_a, 128), bdesc0 = make_desc(0, lbo_b, 128);
+        const uint32_t a_hi = (uint32_t)(adesc0 >> 32), b_hi = (uint32_t)(bdesc0 >> 32);
+        const uint32_t a_kstep = (2u * lbo_a) >> 4, b_kstep = (2u * lbo_b) >> 4;
+        const int nk16 = (ka.debug & 2) ? 0 : ka.KC / 2;
+        const uint32_t a_lo0 = (uint32_t)adesc0 + ((smem_u32(a_smem) & 0x3FFFFu) >> 4);
+        const uint32_t b_lo0 = (uint32_t)bdesc0 + ((smem_u32(b_smem) & 0x3FFFFu) >> 4);
+        const uint32_t a_stage_lo = (uint32_t)ka.a_stage_bytes >> 4, b_stage_lo = (uint32_t)ka.b_stage_bytes >> 4;
+        const uint32_t bnc = (uint32_t)ka.BNC;
+        const uint32_t res_shift = (uint32_t)(-ka.minoff);
+        const int ntaps = a.ntaps, NKB = ka.NKB, NA = ka.NA, NB = ka.NB, NACC = ka.ACC;
+        const bool resident = ka.b_resident != 0;
+        int sa = 0, pa = 0, sb = 0, pb = 0, acc = 0, pacc = 0;
+        uint32_t a_lo_stage = a_lo0, b_lo = b_lo0;
+        uint32_t ph_act = 0, ph_res = 0;   // fused mode: per-stage phase bits of A_FULL / AR_FULL
+        const int nkbt = ka.res_mma ? 2 * NKB : NKB;
+        bool first = true;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+          TRACE(1, 0, t);
+          mbar_wait(T_EMPTY(acc), pacc ^ 1);   // epilogue has drained this accumulator stage
+          TRACE(1, 1, t);
           tc_fence_after();
-          const uint64_t adesc_stage = adesc0 + (a_smem_lo + (uint32_t)sa * a_stage_lo);
-          for (int tap = 0; tap < a.ntaps; ++tap) {
-            if (!ka.b_resident || first) {
-              mbar_wait(B_FULL(sb), pb);
-              tc_fence_after();
+          const uint32_t d0 = tmem_base + (uint32_t)(acc * acc_cols);
+          uint32_t accum = 0;
+          for (int kb = 0; kb < nkbt; ++kb) {
+            const bool is_res = kb >= NKB;   // residual tile x identity weights
+            uint32_t sh = is_res ? res_shift : tapshift[0];
+            if constexpr (FUSE) {
+              if (is_res) { mbar_wait(AR_FULL(sa), (ph_res >> sa) & 1u); ph_res ^= 1u << sa; }
+              else { mbar_wait(A_FULL(sa), (ph_act >> sa) & 1u); ph_act ^= 1u << sa; }
+            } else {
+              mbar_wait(A_FULL(sa), pa);
             }
-            const uint64_t adesc = adesc_stage + (uint32_t)(a.tap_off[tap] - ka.minoff);   // row shift of this tap (>= 0)
-            const uint64_t bdesc = bdesc0 + (b_smem_lo + (uint32_t)sb * b_stage_lo);
-            if (msub == 2) issue_tap<2>(d0, (uint32_t)ka.BNC, adesc, bdesc, idesc, accum, nk16, a_kstep, b_kstep);
-            else if (msub == 4) issue_tap<4>(d0, (uint32_t)ka.BNC, adesc, bdesc, idesc, accum, nk16, a_kstep, b_kstep);
-            else issue_tap<1>(d0, (uint32_t)ka.BNC, adesc, bdesc, idesc, accum, nk16, a_kstep, b_kstep);
-            accum = 1;
-            if (!ka.b_resident) umma_commit(B_EMPTY(sb));
-            if (++sb == ka.NB) { sb = 0; pb ^= 1; }
+            TRACE(1, 2, t);
+            tc_fence_after();
+            const int ntap_kb = is_res ? 1 : ntaps;
+            for (int tap = 0; tap < ntap_kb; ++tap) {
+              const uint32_t sh_next = tapshift[tap + 1];   // one tap ahead: off the critical path
+              if (!resident || first) {
+                mbar_wait(B_FULL(sb), pb);
+                tc_fence_after();
+              }
+              uint32_t alo = a_lo_stage + sh, blo = b_lo;
+              uint32_t af = accum;
+#pragma unroll 2
+              for (int k16 = 0; k16 < nk16; ++k16) {
+                const uint64_t bd = ((uint64_t)b_hi << 32) | blo;
+                umma_bf16(d0, ((uint64_t)a_hi << 32) | alo, bd, idesc, af);
+                if (MS >= 2) umma_bf16(d0 + bnc, ((uint64_t)a_hi << 32) | (alo + 128u), bd, idesc, af);   // +128 rows
+                if (MS == 4) {
+                  umma_bf16(d0 + 2 * bnc, ((uint64_t)a_hi << 32) | (alo + 256u), bd, idesc, af);
+                  umma_bf16(d0 + 3 * bnc, ((uint64_t)a_hi << 32) | (alo + 384u), bd, idesc, af);
+                }
+                alo += a_kstep; blo += b_kstep;
+                af = 1;
+              }
+              accum = 1;
+              if (!resident) umma_commit(B_EMPTY(sb));
+              b_lo += b_stage_lo;
+              if (++sb == NB) { sb = 0; pb ^= 1; b_lo = b_lo0; }
+              sh = sh_next;
+            }
+            umma_commit(A_EMPTY(sa));
+            a_lo_stage += a_stage_lo;
+            if (++sa == NA) { sa = 0; pa ^= 1; a_lo_stage = a_lo0; }
           }
-          umma_commit(A_EMPTY(sa));
-          if (++sa == ka.NA) { sa = 0; pa ^= 1; }
+          umma_commit(T_FULL(acc));
+          TRACE(1, 3, t);
+          if (++acc == NACC) { acc = 0; pacc ^= 1; }
+          first = false;
         }
-        umma_commit(T_FULL(acc));
-        TRACE(1, 3, t);
-        if (++acc == ka.ACC) { acc = 0; pacc ^= 1; }
-        first = false;
-      }
+      };
+      if (ka.MSUB == 4) run(std::integral_constant<int, 4>{});
+      else if (ka.MSUB == 2) run(std::integral_constant<int, 2>{});
+      else run(std::integral_constant<int, 1>{});
     }
     __syncwarp();
-  } else {
+  } else if (warp < 2 + epiw) {
     // ===================== epilogue =====================
     const int quarter = warp & 3;            // TMEM lanes this warp may touch: 32*quarter ..
-    const int half = (warp - 2) >> 2;        // the two warps of a quarter alternate over work items
+    const int half = (warp - 2) >> 2;        // the epiw/4 warps of a quarter alternate over work items
+    constexpr int nsplit = epiw / 4;
     const int ngroups = ka.BNC >> 5;         // 32-column groups per accumulator
     const int nitems = ka.MSUB * ngroups;
     const int N = a.u * a.Cout;
     const bool tr = warp == 2 && lane == 0;
     const bool plain = a.u == 1;
     __nv_bfloat16* yg = reinterpret_cast<__nv_bfloat16*>(a.y);
-    const __nv_bfloat16* rg = reinterpret_cast<const __nv_bfloat16*>(a.res);
+    const __nv_bfloat16* rg = ka.res_mma ? nullptr : reinterpret_cast<const __nv_bfloat16*>(a.res);
     const size_t cs = (size_t)a.Ry * 8;      // elements between consecutive 8-channel chunks
     int acc = 0, pacc = 0;
     int t = blockIdx.x;
@@ -425,7 +545,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UmmaKernel
       mbar_wait(T_FULL(acc), pacc);
       if (tr) TRACE(2, 2, t);
       tc_fence_after();
-      for (int item = half; item < nitems; item += 2) {
+      for (int item = half; item < nitems; item += nsplit) {
         const int sub = item / ngroups, grp = item - sub * ngroups;
         const int q = tl.q0 + sub * 128 + quarter * 32 + lane;
         const bool qok = q < Lqc && !(ka.debug & 1);
@@ -434,35 +554,46 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UmmaKernel
         tmem_ld32_nowait(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * acc_cols + sub * ka.BNC + grp * 32), r);
         const int nbase = n0 + grp * 32;     // first GEMM column of this group
         if (plain) {
-          // plain convolution: output row == q, column == channel; chunk c lives cs elements further
+          // plain convolution: output row == q, column == channel; chunk c lives cs elements further.
+          // Everything that does not depend on the accumulator (bias, residual, old output) is issued
+          // before waiting for the TMEM load, and the four 8-channel chunks are handled branch-free.
           const bool valid = qok && q < soc.len;
           const size_t base = ((size_t)(nbase >> 3) * a.Ry + soc.off + q) * 8;
+          bool ok[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) ok[u] = valid && nbase + 8 * u < N;
+          float4 bv[8];
+          if (use_sbias) {
+            const float4* sb4 = reinterpret_cast<const float4*>(sbias + nbase);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) bv[j] = sb4[j];
+          } else if (biasp) {   // per-segment bias (speaker conditioning) or a very wide layer: same address for the whole warp
+            const float4* gb4 = reinterpret_cast<const float4*>(biasp + nbase);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) bv[j] = nbase + 4 * j < N ? __ldg(gb4 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) bv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
           uint4 resv[4], oldv[4];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            if (valid && nbase + 8 * u < N) {
-              if (rg) resv[u] = *reinterpret_cast<const uint4*>(rg + base + u * cs);
-              if (a.accumulate) oldv[u] = *reinterpret_cast<const uint4*>(yg + base + u * cs);
-            }
+            if (rg && ok[u]) resv[u] = *reinterpret_cast<const uint4*>(rg + base + u * cs);
+            if (a.accumulate && ok[u]) oldv[u] = *reinterpret_cast<const uint4*>(yg + base + u * cs);
           }
           tmem_ld_wait();
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            if (!(valid && nbase + 8 * u < N)) continue;
             float v[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[8 * u + j]);
-            if (biasp) {   // same address for the whole warp: one broadcast L1 transaction
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(biasp + nbase + 8 * u));
-              const float4 b1 = __ldg(reinterpret_cast<const float4*>(biasp + nbase + 8 * u + 4));
-              v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-              v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-            }
-            if (rg) unpack_add(resv[u], v);
+            v[0] = __uint_as_float(r[8 * u + 0]) + bv[2 * u].x; v[1] = __uint_as_float(r[8 * u + 1]) + bv[2 * u].y;
+            v[2] = __uint_as_float(r[8 * u + 2]) + bv[2 * u].z; v[3] = __uint_as_float(r[8 * u + 3]) + bv[2 * u].w;
+            v[4] = __uint_as_float(r[8 * u + 4]) + bv[2 * u + 1].x; v[5] = __uint_as_float(r[8 * u + 5]) + bv[2 * u + 1].y;
+            v[6] = __uint_as_float(r[8 * u + 6]) + bv[2 * u + 1].z; v[7] = __uint_as_float(r[8 * u + 7]) + bv[2 * u + 1].w;
+            if (rg && ok[u]) unpack_add(resv[u], v);
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[j] *= a.out_scale;
-            if (a.accumulate) unpack_add(oldv[u], v);
-            *reinterpret_cast<uint4*>(yg + base + u * cs) = pack8(v);
+            if (a.accumulate && ok[u]) unpack_add(oldv[u], v);
+            if (ok[u]) *reinterpret_cast<uint4*>(yg + base + u * cs) = pack8(v);
           }
         } else {
           // transposed convolution: column n = (phase, channel), output row = q*u + phase - p
@@ -501,14 +632,77 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UmmaKernel
       t = tn;
     }
   }
-  if (ka.trace && blockIdx.x == 0 && warp < 3) {
-    __syncwarp();
-    if (tr_n > 0 || lane == 0) {
-      // the tracing lane of each role flushes its ring (only one lane per role has tr_n > 0)
-      if (tr_n > 0) {
-        ka.trace[warp] = (unsigned long long)tr_n;
-        for (int i = 0; i < tr_n; ++i) ka.trace[4 + warp * 1024 + i] = tr_smem[warp * 1024 + i];
+  else if constexpr (FUSE) {
+    // ===================== activation warps (fused mode) =====================
+    // Raw tile (R stage) -> Activation1d -> activated tile (A stage, UMMA layout).  A work unit is one
+    // 8-channel chunk x ACT_RT consecutive rows; lane = (unit slot tb = lane>>2, channel pair cp).
+    // ACT_RT is odd, so the 8 slots of a warp hit distinct banks with their 4-byte column accesses.
+    const int aw = warp - 2 - epiw;
+    const int cp = lane & 3, tb = lane >> 2;
+    const int rrows = ka.nblk * ACT_RT + 10;
+    int sr = 0, pr = 0, sa = 0, pa = 0;
+    int t = blockIdx.x;
+    TileRef cur = t < total_tiles ? decode(t) : TileRef{0, 0, 0};
+    int Lseg = a.seg_in[cur.b].len;
+    while (t < total_tiles) {
+      const TileRef tl = cur;
+      const int L = Lseg;
+      const int tn = t + gridDim.x;
+      if (tn < total_tiles) { cur = decode(tn); Lseg = a.seg_in[cur.b].len; }
+      const int tA0 = tl.q0 + ka.minoff;      // segment time of A-slab row 0
+      const bool tr = aw == 0 && lane == 0;
+      for (int kb = 0; kb < ka.NKB; ++kb) {
+        const int kcl = (kb == ka.NKB - 1) ? ka.kc_last_load : ka.KC;
+        if (tr) TRACE(3, 0, t);
+        mbar_wait(R_FULL(sr), pr);
+        if (tr) TRACE(3, 1, t);
+        mbar_wait(A_EMPTY(sa), pa ^ 1);
+        if (tr) TRACE(3, 2, t);
+        const __nv_bfloat16* rbase = reinterpret_cast<const __nv_bfloat16*>(r_smem + (size_t)sr * ka.r_stage_bytes);
+        __nv_bfloat16* abase = reinterpret_cast<__nv_bfloat16*>(a_smem + (size_t)sa * ka.a_stage_bytes);
+        const int nunits = kcl * ka.nblk;
+        for (int unit = aw * 8 + tb; unit < nunits; unit += 8 * NACT) {
+          const int c = unit / ka.nblk, blk = unit - c * ka.nblk;
+          const __nv_bfloat16* rcol = rbase + (size_t)(c * ka.rstride) * 8 + 2 * cp;   // slab row 0 of this chunk
+          __nv_bfloat16* ycol = abase + (size_t)(c * ka.astride + blk * ACT_RT) * 8 + 2 * cp;
+          const int ch = (kb * ka.KC + c) * 8 + 2 * cp;
+          const float a0 = 2.f * ka.act_alpha[ch], a1 = 2.f * ka.act_alpha[ch + 1];
+          const float h0 = 0.5f * ka.act_inv_beta[ch], h1 = 0.5f * ka.act_inv_beta[ch + 1];
+          const int r0 = tA0 + blk * ACT_RT;   // segment time of this block's first output
+          if (r0 >= 5 && r0 + ACT_RT + 5 <= L) {   // no replicate padding (input or activated signal) in reach
+            actcore::stream_packed<ACT_RT>(rcol + (size_t)(blk * ACT_RT) * 8, ycol, a0, a1, h0, h1);
+          } else {
+            // block touches a segment end: exact replicate semantics inside [0, L), zero (= the conv's
+            // "same" padding of the ACTIVATED signal) outside
+#pragma unroll 1
+            for (int tt = 0; tt < ACT_RT; ++tt) {
+              const int ts = r0 + tt;
+              float2 v = make_float2(0.f, 0.f);
+              if (ts >= 0 && ts < L) v = actcore::exact_clamped(rcol, tA0 - 5, rrows, ts, L, a0, a1, h0, h1);
+              actcore::stpair(ycol + tt * 8, v);
+            }
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic st.shared -> tcgen05 (async proxy) reads
+        __syncwarp();
+        if (lane == 0) { mbar_arrive(A_FULL(sa)); mbar_arrive(R_EMPTY(sr)); }
+        if (tr) TRACE(3, 3, t);
+        if (++sr == ka.NR) { sr = 0; pr ^= 1; }
+        if (++sa == ka.NA) { sa = 0; pa ^= 1; }
       }
+      if (ka.res_mma)   // the residual k-blocks use the next NKB stages of the A ring
+        for (int kb = 0; kb < ka.NKB; ++kb)
+          if (++sa == ka.NA) { sa = 0; pa ^= 1; }
+      t = tn;
+    }
+  }
+  {
+    // the tracing lane of each role flushes its ring (only one lane per role has tr_n > 0)
+    const int role = warp < 3 ? warp : 3;
+    __syncwarp();
+    if (ka.trace && blockIdx.x == 0 && tr_n > 0) {
+      ka.trace[role] = (unsigned long long)tr_n;
+      for (int i = 0; i < tr_n; ++i) ka.trace[4 + role * 1024 + i] = tr_smem[role * 1024 + i];
     }
   }
   tc_fence_before();
@@ -536,6 +730,27 @@ __global__ void repack_umma_kernel(const float* __restrict__ wt, __nv_bfloat16* 
   int ci = (kb * KC + c) * 8 + e, n = nt * BN + nn;
   float v = (ci < Cin && n < N) ? wt[((size_t)tap * Cin + ci) * N + n] : 0.f;
   img[idx] = __float2bfloat16_rn(v);
+}
+
+// identity images [kb][chunk KC][n BN][8] appended after the conv images of a square (Cin == N), single-n-tile layer
+__global__ void identity_umma_kernel(__nv_bfloat16* __restrict__ img, int N, int KC, int NKB, int BN) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t total = (size_t)NKB * KC * BN * 8;
+  if (idx >= total) return;
+  int e = idx & 7;
+  size_t r = idx >> 3;
+  int nn = r % BN; r /= BN;
+  int c = r % KC;
+  int kb = r / KC;
+  int ci = (kb * KC + c) * 8 + e;
+  img[idx] = __float2bfloat16_rn((ci == nn && nn < N) ? 1.f : 0.f);
+}
+
+bool has_identity(const UmmaTiling& t, int Cin, int N) { return t.ok && t.NT == 1 && Cin == N; }
+
+bool use_res_mma(const ConvArgs& a, const UmmaTiling& t) {
+  static const int maxc = env_int("BVG_RES_MMA_MAXC", 96);
+  return a.res && a.u == 1 && has_identity(t, a.Cin, a.Cout) && a.Cin <= maxc;
 }
 
 void tap_range(const ConvArgs& a, int& mn, int& mx) {
@@ -567,8 +782,9 @@ bool configure(const ConvArgs& a, int msub, UmmaKernelArgs& ka, size_t& smem_byt
   static const int debug_env = env_int("BVG_CONV_DEBUG", 0);
   ka.debug = debug_env;
   ka.trace = nullptr;
+  ka.res_mma = use_res_mma(a, t) ? 1 : 0;
   // pipeline depths within the smem budget
-  const int total_b = t.NKB * a.ntaps;
+  const int total_b = t.NKB * (a.ntaps + ka.res_mma);
   ka.NA = t.NKB > 1 ? 2 : 3;
   ka.b_resident = 0;
   static const int allow_resident = env_int("BVG_CONV_RESIDENT", 1);
@@ -588,8 +804,59 @@ bool configure(const ConvArgs& a, int msub, UmmaKernelArgs& ka, size_t& smem_byt
     ka.NB = nb;
   }
   smem_bytes = (size_t)ka.NA * ka.a_stage_bytes + (size_t)ka.NB * ka.b_stage_bytes +
-               8 * (size_t)(2 * ka.NA + 2 * ka.NB + 2 * ka.ACC) + 16;
+               8 * (size_t)(2 * ka.NA + 2 * ka.NB + 2 * ka.ACC) + 128 + 4 * SBIAS_MAX;
   if (smem_bytes < 120 * 1024) smem_bytes = 120 * 1024;   // one persistent CTA per SM (it owns the TMEM)
+  return smem_bytes <= (size_t)SMEM_MAX;
+}
+
+// Fused (Activation1d in the producer stage) configuration.  Needs the whole N in one CTA tile.
+bool configure_fused(const ConvArgs& a, int msub, UmmaKernelArgs& ka, size_t& smem_bytes) {
+  if (!a.act_alpha || !a.act_inv_beta || a.u != 1) return false;
+  const UmmaTiling t = make_tiling(a.ntaps, a.Cin, a.Cout);
+  if (!t.ok || t.NT != 1) return false;
+  int mn, mx;
+  tap_range(a, mn, mx);
+  if (mx - mn > MAXSPAN || -mn + 5 > BVG_GUARD || mx > BVG_GUARD) return false;
+  ka.c = a;
+  ka.KC = t.KC; ka.NKB = t.NKB; ka.BN = t.BN; ka.BNC = t.BNC; ka.NT = t.NT;
+  ka.minoff = mn; ka.span = mx - mn;
+  ka.MSUB = msub;
+  ka.ACC = 512 / (ka.MSUB * ka.BNC);
+  if (ka.ACC > 4) ka.ACC = 4;
+  if (ka.ACC < 1) return false;
+  ka.tmem_cols = 32;
+  while (ka.tmem_cols < ka.ACC * ka.MSUB * ka.BNC) ka.tmem_cols <<= 1;
+  const int arows = 128 * msub + ka.span;
+  ka.nblk = (arows + ACT_RT - 1) / ACT_RT;
+  ka.astride = ka.nblk * ACT_RT;
+  ka.rstride = ka.nblk * ACT_RT + 10;
+  if (ka.nblk * ACT_RT + 8 > BVG_TAIL_SLACK + BVG_GUARD) return false;   // raw loads past a segment end stay in bounds
+  ka.a_stage_bytes = t.KC * ka.astride * 16;
+  ka.r_stage_bytes = t.KC * ka.rstride * 16;
+  ka.b_stage_bytes = t.KC * t.BN * 16;
+  ka.kc_last_load = a.Cin / 8 - (t.NKB - 1) * t.KC;
+  static const int debug_env = env_int("BVG_CONV_DEBUG", 0);
+  ka.debug = debug_env;
+  ka.trace = nullptr;
+  ka.act_alpha = a.act_alpha; ka.act_inv_beta = a.act_inv_beta;
+  ka.NA = 2; ka.NR = 2;
+  ka.res_mma = use_res_mma(a, t) ? 1 : 0;
+  const size_t fixed = (size_t)ka.NA * ka.a_stage_bytes + (size_t)ka.NR * ka.r_stage_bytes;
+  const int total_b = t.NKB * (a.ntaps + ka.res_mma);
+  ka.b_resident = 0;
+  if (fixed + (size_t)ka.b_stage_bytes > (size_t)SMEM_BUDGET) return false;
+  if (total_b <= MAX_STAGES && fixed + (size_t)total_b * ka.b_stage_bytes <= (size_t)SMEM_BUDGET) {
+    ka.b_resident = 1;
+    ka.NB = total_b;
+  } else {
+    int nb = (int)(((size_t)SMEM_BUDGET - fixed) / ka.b_stage_bytes);
+    if (nb > 8) nb = 8;
+    if (nb > total_b) nb = total_b;
+    if (nb < 2 && total_b >= 2) return false;
+    ka.NB = nb;
+  }
+  smem_bytes = fixed + (size_t)ka.NB * ka.b_stage_bytes + 8 * (size_t)(3 * ka.NA + 2 * ka.NB + 2 * ka.ACC + 2 * ka.NR) + 128 + 4 * SBIAS_MAX;
+  if (smem_bytes < 120 * 1024) smem_bytes = 120 * 1024;
   return smem_bytes <= (size_t)SMEM_MAX;
 }
 
@@ -598,7 +865,7 @@ bool configure(const ConvArgs& a, int msub, UmmaKernelArgs& ka, size_t& smem_byt
 size_t umma_weight_image_bytes(int ntaps, int Cin, int N) {
   UmmaTiling t = make_tiling(ntaps, Cin, N);
   if (!t.ok) return 0;
-  return (size_t)t.NT * t.NKB * ntaps * t.KC * t.BN * 16;
+  return (size_t)(t.NT * t.NKB * ntaps + (has_identity(t, Cin, N) ? t.NKB : 0)) * t.KC * t.BN * 16;
 }
 
 cudaError_t launch_repack_umma(const float* wp_tap_major, void* img, int ntaps, int Cin, int N, cudaStream_t s) {
@@ -607,6 +874,10 @@ cudaError_t launch_repack_umma(const float* wp_tap_major, void* img, int ntaps, 
   size_t total = (size_t)t.NT * t.NKB * ntaps * t.KC * t.BN * 8;
   repack_umma_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(wp_tap_major, (__nv_bfloat16*)img, ntaps, Cin, N,
                                                                     t.KC, t.NKB, t.BN, t.NT);
+  if (has_identity(t, Cin, N)) {
+    const size_t itotal = (size_t)t.NKB * t.KC * t.BN * 8;
+    identity_umma_kernel<<<(unsigned)((itotal + 255) / 256), 256, 0, s>>>((__nv_bfloat16*)img + total, N, t.KC, t.NKB, t.BN);
+  }
   return cudaGetLastError();
 }
 
@@ -627,7 +898,32 @@ int conv_umma_default_msub(const ConvArgs& a) {
   return 1;
 }
 
+// Sub-tiles per tile for the fused kernel, 0 if this layer / geometry cannot be fused.
+int conv_umma_fused_msub(const ConvArgs& a, bool force) {
+  // Opt-in (BVG_FUSE_ACT=1): measured slower than the separate passes on B200 in round 1, because the
+  // activation is FP32-pipe bound and 10 activation warps per SM cannot outrun the stand-alone kernel.
+  static const int enabled = env_int("BVG_FUSE_ACT", 0);
+  static const int forced = env_int("BVG_CONV_MSUB", 0);
+  if (!(enabled || force) || !a.act_alpha) return 0;
+  const UmmaTiling t = make_tiling(a.ntaps, a.Cin, a.Cout);
+  if (!t.ok || t.NT != 1 || a.u != 1) return 0;
+  for (int msub = 4; msub >= 1; msub >>= 1) {
+    if (forced && msub > forced) continue;
+    if (msub > 1 && a.max_q <= 128 * (msub / 2)) continue;
+    if (msub > 1 && msub * t.BNC * 2 > 512) continue;
+    UmmaKernelArgs ka{};
+    size_t smem;
+    if (configure_fused(a, msub, ka, smem)) return msub;
+  }
+  return 0;
+}
+
 bool conv_umma_supported(const ConvArgs& a) {
+  if (a.act_alpha) {
+    UmmaKernelArgs ka{};
+    size_t smem;
+    return a.tile_prefix != nullptr && configure_fused(a, a.msub, ka, smem);
+  }
   UmmaKernelArgs ka{};
   size_t smem;
   return a.tile_prefix != nullptr && (a.msub == 1 || a.msub == 2 || a.msub == 4) && configure(a, a.msub, ka, smem);
@@ -637,7 +933,8 @@ cudaError_t launch_conv_umma(const ConvArgs& a, cudaStream_t s) {
   if (a.B <= 0 || a.max_q <= 0 || a.total_mt <= 0) return cudaSuccess;
   UmmaKernelArgs ka{};
   size_t smem;
-  if (!configure(a, a.msub, ka, smem)) return cudaErrorInvalidValue;
+  const bool fuse = a.act_alpha != nullptr;
+  if (fuse ? !configure_fused(a, a.msub, ka, smem) : !configure(a, a.msub, ka, smem)) return cudaErrorInvalidValue;
   ka.tile_prefix = a.tile_prefix;
   ka.total_mt = a.total_mt;
   static int num_sms = 0;
@@ -645,30 +942,33 @@ cudaError_t launch_conv_umma(const ConvArgs& a, cudaStream_t s) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX);
+    cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX);
     if (e != cudaSuccess) { num_sms = 0; return e; }
   }
   static const int trace_cin = env_int("BVG_CONV_TRACE", 0);   // e.g. 24: trace the first k=3 conv with Cin == 24
   static bool traced = false;
-  const bool do_trace = trace_cin > 0 && !traced && a.Cin == trace_cin && a.u == 1 && a.ntaps == 3;
+  static const int trace_taps = env_int("BVG_CONV_TRACE_TAPS", 3);
+  const bool do_trace = trace_cin > 0 && !traced && a.Cin == trace_cin && a.u == 1 && a.ntaps == trace_taps;
   if (do_trace) {
-    cudaMalloc((void**)&ka.trace, (4 + 3 * 1024) * 8);
-    cudaMemset(ka.trace, 0, (4 + 3 * 1024) * 8);
+    cudaMalloc((void**)&ka.trace, (4 + 4 * 1024) * 8);
+    cudaMemset(ka.trace, 0, (4 + 4 * 1024) * 8);
     traced = true;
     smem = SMEM_MAX;
   }
   const int total_tiles = ka.total_mt * ka.NT;
-  dim3 grid(total_tiles < num_sms ? total_tiles : num_sms), block(NTHREADS);
-  conv_umma_kernel<<<grid, block, smem, s>>>(ka);
+  dim3 grid(total_tiles < num_sms ? total_tiles : num_sms), block(fuse ? NTHREADS_FUSED : NTHREADS);
+  if (fuse) conv_umma_kernel<true><<<grid, block, smem, s>>>(ka);
+  else conv_umma_kernel<false><<<grid, block, smem, s>>>(ka);
   if (do_trace) {
     cudaStreamSynchronize(s);
-    static unsigned long long h[4 + 3 * 1024];
+    static unsigned long long h[4 + 4 * 1024];
     cudaMemcpy(h, ka.trace, sizeof h, cudaMemcpyDeviceToHost);
     FILE* f = fopen("gpurun_out/conv_trace.txt", "w");
     if (f) {
       fprintf(f, "# NA %d NB %d ACC %d MSUB %d BN %d KC %d NKB %d resident %d tiles %d grid %d\n", ka.NA, ka.NB, ka.ACC,
               ka.MSUB, ka.BN, ka.KC, ka.NKB, ka.b_resident, total_tiles, (int)grid.x);
-      for (int role = 0; role < 3; ++role)
+      for (int role = 0; role < 4; ++role)
         for (unsigned long long i = 0; i < h[role] && i < 1024; ++i) {
           unsigned long long v = h[4 + role * 1024 + i];
           fprintf(f, "%d %llu %llu %llu\n", role, v >> 56, (v >> 40) & 0xffff, v & 0xffffffffffULL);

@@ -60,6 +60,20 @@ def conv1d(x, w, b, res, k, d, mode):
     return y.cpu().numpy()
 
 
+def act_conv1d(x, la, lb, w, b, res, k, d, mode, want_fused=False):
+    xt, wt, lat, lbt = dev(x), dev(w), dev(la), dev(lb)
+    bt = None if b is None else dev(b)
+    rt = None if res is None else dev(res)
+    B, Cin, T = xt.shape
+    Cout = wt.shape[0]
+    y = torch.empty(B, Cout, T, device="cuda")
+    fused = C.c_int32(1 if want_fused else 0)   # in: request the fused kernel, out: whether it ran
+    lib.check(L_().bvg_act_conv1d(ptr(xt), ptr(lat), ptr(lbt), ptr(wt), ptr(bt), ptr(rt), ptr(y), B, Cin, Cout, T, k, d,
+                                  mode, C.addressof(fused), stream()))
+    torch.cuda.synchronize()
+    return y.cpu().numpy(), bool(fused.value)
+
+
 def conv_transpose1d(x, w, b, k, u, mode):
     xt, wt = dev(x), dev(w)
     bt = None if b is None else dev(b)

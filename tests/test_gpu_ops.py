@@ -147,3 +147,51 @@ def test_conv_transpose1d_tcgen05_bf16(case):
     y = G.conv_transpose1d(x, w, b, k, u, 1)
     scale = np.abs(ref).max()
     assert np.abs(y - ref).max() <= 8e-3 * scale, (np.abs(y - ref).max(), scale)
+
+
+ACT_CONV_CASES = [  # (B, C, T, k, d): AMPBlock1 half-steps (Activation1d -> Conv1d [+ residual])
+    (1, 24, 700, 3, 1), (1, 24, 100, 11, 5), (2, 48, 333, 7, 3), (2, 96, 300, 11, 5), (1, 192, 400, 3, 1),
+    (3, 24, 7, 3, 1), (1, 384, 90, 7, 1),
+]
+
+
+@pytest.mark.parametrize("case", ACT_CONV_CASES)
+@pytest.mark.parametrize("want_fused", [False, True])
+@pytest.mark.parametrize("with_res", [False, True])
+def test_act_conv1d_tcgen05_bf16(case, want_fused, with_res):
+    """Activation1d + conv through both bf16 paths: separate passes (what bvg_forward runs) and the
+    experimental producer-fused kernel; layers the fused kernel does not cover must fall back."""
+    from tests import gpu_util as G
+    B, C, T, k, d = case
+    rng = np.random.default_rng(11)
+    x = rng.standard_normal((B, C, T)).astype(np.float32)
+    la = (0.3 * rng.standard_normal(C)).astype(np.float32)
+    lb = (0.3 * rng.standard_normal(C)).astype(np.float32)
+    w = (rng.standard_normal((C, C, k)) / np.sqrt(C * k)).astype(np.float32)
+    b = (0.1 * rng.standard_normal(C)).astype(np.float32)
+    r = rng.standard_normal((B, C, T)).astype(np.float32) if with_res else None
+    act = O.activation1d(G.bf16_round(x), la.astype(np.float64), lb.astype(np.float64))
+    ref = O.conv1d(G.bf16_round(act), G.bf16_round(w), b.astype(np.float64), dilation=d, padding=O.get_padding(k, d))
+    if with_res:
+        ref = ref + G.bf16_round(r)
+    y, fused = G.act_conv1d(x, la, lb, w, b, r, k, d, 1, want_fused=want_fused)
+    assert fused == (want_fused and C <= 256)
+    scale = np.abs(ref).max()
+    # the activated tensor is rounded to bf16 before the MMA on both paths; allow one more rounding step
+    assert np.abs(y - ref).max() <= 1.6e-2 * scale, (np.abs(y - ref).max(), scale)
+
+
+def test_act_conv1d_cuda_core_fp32():
+    from tests import gpu_util as G
+    B, C, T, k, d = 2, 24, 211, 7, 3
+    rng = np.random.default_rng(12)
+    x = rng.standard_normal((B, C, T)).astype(np.float32)
+    la = (0.3 * rng.standard_normal(C)).astype(np.float32)
+    lb = (0.3 * rng.standard_normal(C)).astype(np.float32)
+    w = (rng.standard_normal((C, C, k)) / np.sqrt(C * k)).astype(np.float32)
+    b = (0.1 * rng.standard_normal(C)).astype(np.float32)
+    ref = O.conv1d(O.activation1d(x.astype(np.float64), la.astype(np.float64), lb.astype(np.float64)),
+                   w.astype(np.float64), b.astype(np.float64), dilation=d, padding=O.get_padding(k, d))
+    y, fused = G.act_conv1d(x, la, lb, w, b, None, k, d, 0, want_fused=True)
+    assert not fused
+    np.testing.assert_allclose(y, ref, atol=3e-5, rtol=1e-5)
