@@ -522,6 +522,7 @@ __global__ void __launch_bounds__(FUSE ? NTHREADS_FUSED : NTHREADS, 1) conv_umma
     const bool plain = a.u == 1;
     __nv_bfloat16* yg = reinterpret_cast<__nv_bfloat16*>(a.y);
     const __nv_bfloat16* rg = ka.res_mma ? nullptr : reinterpret_cast<const __nv_bfloat16*>(a.res);
+    const bool simple = plain && use_sbias && rg == nullptr && !a.accumulate;
     const size_t cs = (size_t)a.Ry * 8;      // elements between consecutive 8-channel chunks
     int acc = 0, pacc = 0;
     int t = blockIdx.x;
@@ -553,7 +554,27 @@ __global__ void __launch_bounds__(FUSE ? NTHREADS_FUSED : NTHREADS, 1) conv_umma
         __syncwarp();   // tcgen05.ld is .sync.aligned: reconverge after the predicated stores below
         tmem_ld32_nowait(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * acc_cols + sub * ka.BNC + grp * 32), r);
         const int nbase = n0 + grp * 32;     // first GEMM column of this group
-        if (plain) {
+        if (simple) {
+          // fast path (no residual / accumulate reads, batch-independent bias in shared memory): the
+          // common case of the AMP-block convolutions -- bias, scale, convert, four 16-byte stores
+          const bool valid = qok && q < soc.len;
+          __nv_bfloat16* yp = yg + ((size_t)(nbase >> 3) * a.Ry + soc.off + q) * 8;
+          const float4* sb4 = reinterpret_cast<const float4*>(sbias + nbase);
+          float4 bv[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) bv[j] = sb4[j];
+          const float osc = a.out_scale;
+          tmem_ld_wait();
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            float v[8];
+            v[0] = (__uint_as_float(r[8 * u + 0]) + bv[2 * u].x) * osc; v[1] = (__uint_as_float(r[8 * u + 1]) + bv[2 * u].y) * osc;
+            v[2] = (__uint_as_float(r[8 * u + 2]) + bv[2 * u].z) * osc; v[3] = (__uint_as_float(r[8 * u + 3]) + bv[2 * u].w) * osc;
+            v[4] = (__uint_as_float(r[8 * u + 4]) + bv[2 * u + 1].x) * osc; v[5] = (__uint_as_float(r[8 * u + 5]) + bv[2 * u + 1].y) * osc;
+            v[6] = (__uint_as_float(r[8 * u + 6]) + bv[2 * u + 1].z) * osc; v[7] = (__uint_as_float(r[8 * u + 7]) + bv[2 * u + 1].w) * osc;
+            if (valid && nbase + 8 * u < N) *reinterpret_cast<uint4*>(yp + u * cs) = pack8(v);
+          }
+        } else if (plain) {
           // plain convolution: output row == q, column == channel; chunk c lives cs elements further.
           // Everything that does not depend on the accumulator (bias, residual, old output) is issued
           // before waiting for the TMEM load, and the four 8-channel chunks are handled branch-free.
