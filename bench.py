@@ -2,7 +2,7 @@
 """bench.py -- BigVGAN2 speech-code decode throughput on B200 (BASELINE.json metric).
 
     python bench.py --gpus N --steps K --warmup W            # our arm (one rank per GPU under torchrun)
-    python bench.py --impl reference --steps K --warmup W    # CPU reference arm (oracle port)
+    python bench.py --impl reference --steps K --warmup W    # CPU reference arm (torch-CPU port)
 
 A "step" is one decode of the configuration BASELINE.json quotes the metric on: config 2,
 batch 16 x 10 s of synthetic latents (T = 235 frames -> 240 640 samples each), bf16 tensor-core
@@ -76,35 +76,39 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU reference arm / cpu_baseline: the oracle port (numpy restatement of the reference's torch path)
+# CPU reference arm / cpu_baseline: the CPU port of the reference path (oracle/bigvgan_torch_cpu.py)
 # ------------------------------------------------------------------------------------------------
 def cpu_decode_rate(sample_frames: int, repeats: int, warmup: int):
-    """Times oracle.bigvgan_forward_with_embedding (fp32) on B=1 x sample_frames latent frames.
-    Returns (audio-seconds per second, per-step seconds, cores)."""
-    from oracle import bigvgan_oracle as O          # the ONLY place bench.py executes oracle/
+    """Times the CPU port of the reference path (oracle/bigvgan_torch_cpu.py: the reference's own torch
+    operators on the host cores, fp32, all threads) on B=1 x sample_frames latent frames.
+    Returns (audio-seconds per second, per-step seconds, threads used)."""
+    import torch
+    from oracle import bigvgan_torch_cpu as TC      # the ONLY place bench.py executes oracle/
     from b200vgan import synth
-    sd = synth.make_state_dict(1234, with_speaker_encoder=False)
-    sd = {k: np.asarray(v, np.float32) for k, v in sd.items()}
+    sd = TC.prepare_state_dict(synth.make_state_dict(1234, with_speaker_encoder=False))
     emb = synth.make_speaker_embedding(B=1)
     times = []
     for i in range(warmup + repeats):
         x = synth.make_latents(2, i, 1, sample_frames)
         t0 = time.perf_counter()
-        O.bigvgan_forward_with_embedding(x, emb, sd, dtype=np.float32)
+        TC.bigvgan_forward_with_embedding(x, emb, sd)
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
     audio_s = sample_frames * HOP / SR
-    return audio_s * len(times) / sum(times), sum(times) / len(times), os.cpu_count()
+    return audio_s * len(times) / sum(times), sum(times) / len(times), torch.get_num_threads()
+
+
+CPU_PORT = "torch-CPU port of the reference path (same F.conv1d/conv_transpose1d operators, oneDNN, fp32)"
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    frames = 12
+    frames = 47
     rate, step_s, cores = cpu_decode_rate(frames, max(1, args.steps), max(0, args.warmup))
-    sample = f"B=1 x {frames} latent frames ({frames * HOP / SR:.2f} s audio) per step, numpy fp32 oracle port, all host threads"
+    sample = f"B=1 x {frames} latent frames ({frames * HOP / SR:.2f} s audio) per step, {CPU_PORT}, {cores} threads"
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True,
@@ -232,11 +236,11 @@ def run_ours(args):
         }
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            frames = 24
-            rate, step_s, cores = cpu_decode_rate(frames, 3, 1)
+            frames = 47
+            rate, step_s, cores = cpu_decode_rate(frames, 4, 1)
             cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": f"B=1 x {frames} latent frames ({frames * HOP / SR:.2f} s audio), numpy fp32 oracle port, "
-                             f"best-effort all host threads, mean of 3 after 1 warm-up"}
+                   "sample": f"B=1 x {frames} latent frames ({frames * HOP / SR:.2f} s audio), {CPU_PORT}, "
+                             f"{cores} threads, mean of 4 after 1 warm-up"}
         launches = g.num_launches([T] * B) * args.steps
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,

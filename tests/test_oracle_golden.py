@@ -90,3 +90,18 @@ def test_conv_transpose_closed_form():
                         if q - m >= 0:
                             y2[0, :, n] += w[:, :, phi + m * u].T @ xp[0, :, q - m]
         np.testing.assert_allclose(y2, y, atol=1e-12)
+
+
+def test_torch_cpu_port_matches_reference_golden(golden_dir):
+    """The CPU baseline port (what bench.py's reference arm times) reproduces the unmodified reference."""
+    import torch
+    from oracle import bigvgan_torch_cpu as TC
+    from b200vgan import synth
+    g = np.load(os.path.join(golden_dir, "forward_tiny.npz"))
+    sd = synth.make_state_dict(1234, with_speaker_encoder=False)
+    y32 = TC.bigvgan_forward_with_embedding(g["x"], g["emb"], TC.prepare_state_dict(sd))
+    np.testing.assert_allclose(y32, g["wav"], atol=2e-5)
+    y64 = TC.bigvgan_forward_with_embedding(g["x"], g["emb"], TC.prepare_state_dict(sd, torch.float64), dtype=torch.float64)
+    assert np.abs(y64 - g["wav64"]).max() < 2e-6      # the stored embedding is the reference's fp32 one
+    yo = O.bigvgan_forward_with_embedding(g["x"], g["emb"], sd)
+    assert np.abs(y64 - yo).max() < 1e-12            # torch port == numpy oracle on identical inputs
