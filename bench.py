@@ -85,6 +85,9 @@ def cpu_decode_rate(sample_frames: int, repeats: int, warmup: int):
     import torch
     from oracle import bigvgan_torch_cpu as TC      # the ONLY place bench.py executes oracle/
     from b200vgan import synth
+    # torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core it can
+    ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    torch.set_num_threads(max(1, ncpu))
     sd = TC.prepare_state_dict(synth.make_state_dict(1234, with_speaker_encoder=False))
     emb = synth.make_speaker_embedding(B=1)
     times = []

@@ -61,6 +61,7 @@ typedef struct bvg_config {
   int32_t num_dilations;             /* 3                                          */
   int32_t speaker_embedding_dim;     /* 512                                        */
   int32_t cond_in_each_up_layer;     /* 1                                          */
+  int32_t num_mels;                  /* 100   input width of the speaker encoder (0 = 100) */
 } bvg_config;
 
 typedef struct bvg_handle bvg_handle;
@@ -82,8 +83,9 @@ void bvg_destroy(bvg_handle* h);
  * "conv_pre.weight" [1536,1024,7], "ups.0.0.weight" [1536,768,8] (ConvTranspose1d layout
  * [Cin,Cout,k]), "resblocks.4.convs1.2.bias", "resblocks.0.activations.3.act.alpha" (log scale),
  * "cond_layer.weight", "conds.2.bias", "conv_post.weight".  `data` may be a host or a device
- * pointer (is_device).  Unknown names are an error; "speaker_encoder.*" and "*.filter" are not
- * accepted here (the filter taps are architecture constants, models.py never trains them). */
+ * pointer (is_device).  Unknown names are an error; "*.filter" buffers are not accepted (the filter
+ * taps are architecture constants, models.py never trains them).  "speaker_encoder.*" parameters
+ * are optional as a group: upload all of them to use bvg_speaker_embedding, or none. */
 int bvg_set_weight(bvg_handle* h, const char* name, const float* data, const int64_t* shape,
                    int32_t ndim, int32_t is_device, void* stream);
 
@@ -134,6 +136,19 @@ int bvg_workspace_reset(bvg_handle* h);
 int bvg_forward_host(bvg_handle* h, bvg_plan* plan, const void* latent_host, int32_t latent_dtype,
                      void* latent_dev, const float* spk_emb, int32_t spk_batch, float* wav_host,
                      float* wav_dev, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- speaker encoder ------------------------------------------------------------------------
+ * Replaces `speaker_embedding = self.speaker_encoder(mel_ref, lens)` (models.py:202-208; ECAPA-TDNN,
+ * ECAPA_TDNN.py:429-581, fp32).  Needs every "speaker_encoder.*" parameter of the checkpoint uploaded
+ * with bvg_set_weight before bvg_finalize (the BatchNorm "num_batches_tracked" counters are not
+ * parameters and are not accepted).
+ *   mel       [B, Tm, num_mels] fp32 device, Tm >= 5
+ *   rel_lens  [B] fp32 device (relative lengths in (0,1], the reference's `lens`) or NULL
+ *   emb       [B, 1, speaker_embedding_dim] fp32 device -- feed it to bvg_forward as spk_emb
+ *   workspace >= bvg_ecapa_workspace_bytes(h, B, Tm) bytes of device memory */
+size_t bvg_ecapa_workspace_bytes(const bvg_handle* h, int32_t B, int32_t Tm);
+int bvg_speaker_embedding(bvg_handle* h, const float* mel, int32_t B, int32_t Tm, const float* rel_lens,
+                          float* emb, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- per-op entry points (drop-in for the reference's native extension, and test hooks) ----
  *

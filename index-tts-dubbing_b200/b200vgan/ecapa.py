@@ -1,11 +1,11 @@
-"""ECAPA-TDNN speaker encoder (mel [B',Tm,100] -> embedding [B',1,512]) -- interim torch-op version.
+"""ECAPA-TDNN speaker encoder: PARAMETER CONTAINER with the reference's state-dict key layout.
 
-SURVEY.md section 8(f) row 1 lists a native ECAPA as the NEXT component after the generator hot
-path; until then the encoder runs as plain torch ops on the GPU (it is ~0.05 % of the decode FLOPs
-and its result is a per-prompt constant that `BigVGAN` caches).  The module tree reproduces the
-reference's state-dict key layout (reference: indextts/BigVGAN/ECAPA_TDNN.py:429-541, 231 keys,
-e.g. ``blocks.1.res2net_block.blocks.3.norm.norm.running_var``) so reference checkpoints load
-unchanged; the forward restates ECAPA_TDNN.py:543-581.
+The product path does not run this module: `BigVGAN.speaker_embedding` uploads these tensors to
+libb200vgan.so and calls `bvg_speaker_embedding` (csrc/bvg_ecapa.cu, fp32 CUDA kernels).  The module
+tree reproduces the reference's key layout (reference: indextts/BigVGAN/ECAPA_TDNN.py:429-541, 231
+keys, e.g. ``blocks.1.res2net_block.blocks.3.norm.norm.running_var``) so reference checkpoints load
+unchanged with ``load_state_dict(strict=True)``.  `forward` restates ECAPA_TDNN.py:543-581 with torch
+operators and is kept only as a debugging aid for tests; nothing in b200vgan calls it.
 """
 from __future__ import annotations
 

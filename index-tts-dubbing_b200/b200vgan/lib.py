@@ -20,7 +20,7 @@ SYMBOLS = [
     "bvg_finalize", "bvg_plan_create", "bvg_plan_destroy", "bvg_plan_workspace_bytes", "bvg_plan_max_frames",
     "bvg_plan_num_launches", "bvg_forward", "bvg_forward_host", "bvg_activation1d", "bvg_conv1d",
     "bvg_conv_transpose1d", "bvg_workspace_reset", "bvg_profile_enable", "bvg_profile_read",
-    "bvg_activation1d_packed", "bvg_act_conv1d",
+    "bvg_activation1d_packed", "bvg_act_conv1d", "bvg_ecapa_workspace_bytes", "bvg_speaker_embedding",
 ]
 
 
@@ -37,6 +37,7 @@ class BvgConfig(C.Structure):
         ("num_dilations", C.c_int32),
         ("speaker_embedding_dim", C.c_int32),
         ("cond_in_each_up_layer", C.c_int32),
+        ("num_mels", C.c_int32),
     ]
 
 
@@ -81,6 +82,9 @@ def load(rebuild: bool = False) -> C.CDLL:
     lib.bvg_activation1d_packed.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp]
     lib.bvg_conv1d.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp]
     lib.bvg_act_conv1d.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp]
+    lib.bvg_ecapa_workspace_bytes.argtypes = [vp, i32, i32]
+    lib.bvg_ecapa_workspace_bytes.restype = sz
+    lib.bvg_speaker_embedding.argtypes = [vp, vp, i32, i32, vp, vp, vp, sz, vp]
     lib.bvg_conv_transpose1d.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp]
     _lib = lib
     return lib
@@ -123,4 +127,5 @@ def make_config(h) -> BvgConfig:
             cfg.resblock_dilation_sizes[j][m] = int(d)
     cfg.speaker_embedding_dim = int(get("speaker_embedding_dim"))
     cfg.cond_in_each_up_layer = 1 if get("cond_d_vector_in_each_upsampling_layer", True) else 0
+    cfg.num_mels = int(get("num_mels", 100))
     return cfg

@@ -201,8 +201,22 @@ class BigVGAN(nn.Module):
         if cache_key is not None and cache_key in self._spk_cache:
             return self._spk_cache[cache_key]
         dev = self.conv_pre.bias.device
-        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):   # keep the embedding fp32-exact
-            emb = self.speaker_encoder(mel_ref.to(dev), None if lens is None else lens.to(dev)).float().contiguous()
+        if dev.type != "cuda":
+            raise _lib.BvgError("b200vgan has no CPU path: move the module to a CUDA (sm_100) device first")
+        mel = mel_ref.to(device=dev, dtype=torch.float32).contiguous()
+        Bp, Tm, M = mel.shape
+        if M != self._cfg.num_mels:
+            raise _lib.BvgError(f"mel width {M} != num_mels {self._cfg.num_mels}")
+        rl = None if lens is None else torch.as_tensor(lens, dtype=torch.float32).to(dev).contiguous()
+        with torch.cuda.device(dev):
+            self._ensure_engine(dev)
+            nbytes = int(self._libh.bvg_ecapa_workspace_bytes(self._handle, Bp, Tm))
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            emb = torch.empty(Bp, 1, self._cfg.speaker_embedding_dim, device=dev, dtype=torch.float32)
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _lib.check(self._libh.bvg_speaker_embedding(self._handle, mel.data_ptr(), Bp, Tm,
+                                                        None if rl is None else rl.data_ptr(), emb.data_ptr(),
+                                                        ws.data_ptr(), nbytes, stream))
         if cache_key is not None:
             self._spk_cache[cache_key] = emb
         return emb
@@ -272,6 +286,10 @@ class BigVGAN(nn.Module):
             for i, c in enumerate(self.conds):
                 out[f"conds.{i}.weight"] = c.weight.detach()
                 out[f"conds.{i}.bias"] = c.bias.detach()
+        # speaker encoder: parameters and BatchNorm running statistics under their checkpoint names
+        for k, v in self.speaker_encoder.state_dict().items():
+            if not k.endswith("num_batches_tracked"):
+                out["speaker_encoder." + k] = v.detach()
         return out
 
     def _ensure_engine(self, device):

@@ -16,6 +16,7 @@
 
 #include "../../include/b200vgan.h"
 #include "bvg_common.cuh"
+#include "bvg_ecapa.cuh"
 #include "bvg_misc.cuh"
 
 namespace {
@@ -98,6 +99,11 @@ struct bvg_handle {
   CondLayer cond_pre;
   std::vector<CondLayer> conds;
   std::map<std::string, ParamSlot> params;
+  // ECAPA-TDNN speaker encoder ("speaker_encoder.*" keys): optional -- a caller that supplies its own
+  // embedding never uploads them; bvg_speaker_embedding needs all of them
+  EcapaModel ecapa;
+  std::map<std::string, ParamSlot> ecapa_params;
+  bool ecapa_ready = false;
   std::vector<void*> owned;
   std::map<const void*, uint64_t> ws_owner;   // workspace -> uid of the plan whose guard rows it holds
   bool finalized = false;
@@ -345,6 +351,13 @@ int bvg_create(const bvg_config* cfg, bvg_handle** out) {
   h->conv_post.Cin = ch; h->conv_post.Cout = 1; h->conv_post.k = 7; h->conv_post.setup();
   add_conv_params(h, "conv_post", h->conv_post);
   if (ch > 64) { delete h; return fail("bvg_create: conv_post supports at most 64 input channels"); }
+  ecapa_register(h->ecapa, cfg->num_mels > 0 ? cfg->num_mels : 100, D,
+                 [h](const std::string& name, float** dst, std::vector<long long> shape) {
+                   ParamSlot sl;
+                   sl.dst = dst;
+                   sl.shape.assign(shape.begin(), shape.end());
+                   h->ecapa_params["speaker_encoder." + name] = sl;
+                 });
   *out = h;
   return 0;
 }
@@ -360,7 +373,10 @@ int bvg_set_weight(bvg_handle* h, const char* name, const float* data, const int
                    int32_t is_device, void* stream) {
   if (!h || !name || !data) return fail("bvg_set_weight: null argument");
   auto it = h->params.find(name);
-  if (it == h->params.end()) return fail("bvg_set_weight: unknown parameter '%s'", name);
+  if (it == h->params.end()) {
+    it = h->ecapa_params.find(name);
+    if (it == h->ecapa_params.end()) return fail("bvg_set_weight: unknown parameter '%s'", name);
+  }
   ParamSlot& s = it->second;
   size_t n = 1;
   bool ok = (size_t)ndim == s.shape.size();
@@ -428,8 +444,52 @@ int bvg_finalize(bvg_handle* h, void* stream) {
   for (auto& L : h->c2) if (finalize_conv(h, L, s, true)) return 1;
   for (auto& A : h->acts) if (finalize_act(h, A, s)) return 1;
   if (finalize_act(h, h->act_post, s)) return 1;
+  // speaker encoder: all-or-nothing
+  size_t nset = 0;
+  for (auto& kv : h->ecapa_params) nset += kv.second.set ? 1 : 0;
+  h->ecapa_ready = false;
+  if (nset) {
+    for (auto& kv : h->ecapa_params)
+      if (!kv.second.set) return fail("bvg_finalize: speaker-encoder parameter '%s' was never set", kv.first.c_str());
+    std::vector<EcapaTdnn*> tdnns;
+    ecapa_collect_bn(h->ecapa, tdnns);
+    for (EcapaTdnn* t : tdnns) {
+      if (!t->scale) {
+        void* p = nullptr;
+        if (dev_alloc(h, &p, 2 * (size_t)t->cout * sizeof(float))) return 1;
+        t->scale = (float*)p; t->shift = t->scale + t->cout;
+      }
+      CK(ecapa_fold_bn(t->bn_w, t->bn_b, t->bn_m, t->bn_v, t->scale, t->shift, t->cout, s));
+    }
+    const int c6 = 6 * h->ecapa.C;
+    if (!h->ecapa.abn_scale) {
+      void* p = nullptr;
+      if (dev_alloc(h, &p, 2 * (size_t)c6 * sizeof(float))) return 1;
+      h->ecapa.abn_scale = (float*)p; h->ecapa.abn_shift = h->ecapa.abn_scale + c6;
+    }
+    CK(ecapa_fold_bn(h->ecapa.abn_w, h->ecapa.abn_b, h->ecapa.abn_m, h->ecapa.abn_v, h->ecapa.abn_scale, h->ecapa.abn_shift, c6, s));
+    h->ecapa_ready = true;
+  }
   CK(cudaStreamSynchronize(s));
   h->finalized = true;
+  return 0;
+}
+
+size_t bvg_ecapa_workspace_bytes(const bvg_handle* h, int32_t B, int32_t Tm) {
+  if (!h || B < 1 || Tm < 1) return 0;
+  return ecapa_workspace_bytes(h->ecapa, B, Tm);
+}
+
+int bvg_speaker_embedding(bvg_handle* h, const float* mel, int32_t B, int32_t Tm, const float* rel_lens, float* emb,
+                          void* workspace, size_t workspace_bytes, void* stream) {
+  if (!h || !mel || !emb || !workspace) return fail("bvg_speaker_embedding: null argument");
+  if (bvg_device_check()) return 1;
+  if (!h->finalized || !h->ecapa_ready)
+    return fail("bvg_speaker_embedding: the speaker_encoder.* parameters were not uploaded (bvg_set_weight) before bvg_finalize");
+  if (B < 1 || Tm < 5) return fail("bvg_speaker_embedding: need B >= 1 and at least 5 mel frames (reflect padding), got B=%d Tm=%d", B, Tm);
+  if (workspace_bytes < ecapa_workspace_bytes(h->ecapa, B, Tm)) return fail("bvg_speaker_embedding: workspace too small");
+  int launches = 0;
+  CK(ecapa_forward(h->ecapa, mel, B, Tm, rel_lens, emb, workspace, (cudaStream_t)stream, &launches));
   return 0;
 }
 

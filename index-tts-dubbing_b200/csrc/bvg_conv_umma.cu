@@ -340,15 +340,18 @@ __global__ void __launch_bounds__(FUSE ? NTHREADS_FUSED : NTHREADS, 1) conv_umma
       const __nv_bfloat16* resg = reinterpret_cast<const __nv_bfloat16*>(a.res);
       long long row0 = t < total_tiles ? (long long)a.seg_in[cur.b].off + cur.q0 + ka.minoff : 0;
       long long rrow0 = t < total_tiles ? (long long)a.seg_out[cur.b].off + cur.q0 : 0;
+      int seglen = (FUSE && t < total_tiles) ? a.seg_in[cur.b].len : 0;
       while (t < total_tiles) {
         TRACE(0, 0, t);
         const int tn = t + gridDim.x;
         const int nt = cur.nt;
         const long long row0c = row0, rrow0c = rrow0;
+        const int Lc = seglen, q0c = cur.q0;
         if (tn < total_tiles) {   // prefetch the next tile's coordinates
           cur = decode(tn);
           row0 = (long long)a.seg_in[cur.b].off + cur.q0 + ka.minoff;
           rrow0 = (long long)a.seg_out[cur.b].off + cur.q0;
+          if (FUSE) seglen = a.seg_in[cur.b].len;
         }
         for (int kb = 0; kb < ka.NKB; ++kb) {
           const int kcl = (kb == ka.NKB - 1) ? ka.kc_last_load : ka.KC;
@@ -359,9 +362,21 @@ __global__ void __launch_bounds__(FUSE ? NTHREADS_FUSED : NTHREADS, 1) conv_umma
             TRACE(0, 2, t);
             mbar_expect_tx(R_FULL(sr), (uint32_t)(kcl * rrows * 16));
             const uint32_t rdst = smem_u32(r_smem + (size_t)sr * ka.r_stage_bytes);
+            // Slab row j holds segment time tR0 + j.  The five rows on either side of the segment carry
+            // the replicate padding of Activation1d's input (x[0] / x[L-1]) instead of the layout's zero
+            // guard rows, so the activation warps can stream every block with the interior formulas; the
+            // pieces are disjoint (no ordering exists between bulk copies).  Interior tiles: one piece.
+            const int tR0 = q0c + ka.minoff - 5;
+            auto clampj = [&](int v) { return v < 0 ? 0 : (v > rrows ? rrows : v); };
+            const int jl0 = clampj(-5 - tR0), jl1 = clampj(-tR0), jr0 = clampj(Lc - tR0), jr1 = clampj(Lc + 5 - tR0);
             for (int c = 0; c < kcl; ++c) {
-              const __nv_bfloat16* src = xg + ((size_t)(kb * ka.KC + c) * a.Rx + row0c - 5) * 8;
-              bulk_g2s(rdst + (uint32_t)(c * ka.rstride) * 16, src, (uint32_t)(rrows * 16), R_FULL(sr));
+              const __nv_bfloat16* src = xg + ((size_t)(kb * ka.KC + c) * a.Rx + row0c - 5) * 8;   // slab row 0
+              const uint32_t dst = rdst + (uint32_t)(c * ka.rstride) * 16;
+              if (jl0 > 0) bulk_g2s(dst, src, (uint32_t)(jl0 * 16), R_FULL(sr));
+              for (int j = jl0; j < jl1; ++j) bulk_g2s(dst + j * 16, src + (size_t)(-tR0) * 8, 16u, R_FULL(sr));          // x[0]
+              if (jr0 > jl1) bulk_g2s(dst + jl1 * 16, src + (size_t)jl1 * 8, (uint32_t)((jr0 - jl1) * 16), R_FULL(sr));
+              for (int j = jr0; j < jr1; ++j) bulk_g2s(dst + j * 16, src + (size_t)(Lc - 1 - tR0) * 8, 16u, R_FULL(sr));  // x[L-1]
+              if (rrows > jr1) bulk_g2s(dst + jr1 * 16, src + (size_t)jr1 * 8, (uint32_t)((rrows - jr1) * 16), R_FULL(sr));
             }
             if (++sr == ka.NR) { sr = 0; pr ^= 1; }
             if (++sa == ka.NA) { sa = 0; pa ^= 1; }   // the activation warps fill this A stage
@@ -690,17 +705,23 @@ __global__ void __launch_bounds__(FUSE ? NTHREADS_FUSED : NTHREADS, 1) conv_umma
           const float a0 = 2.f * ka.act_alpha[ch], a1 = 2.f * ka.act_alpha[ch + 1];
           const float h0 = 0.5f * ka.act_inv_beta[ch], h1 = 0.5f * ka.act_inv_beta[ch + 1];
           const int r0 = tA0 + blk * ACT_RT;   // segment time of this block's first output
-          if (r0 >= 5 && r0 + ACT_RT + 5 <= L) {   // no replicate padding (input or activated signal) in reach
-            actcore::stream_packed<ACT_RT>(rcol + (size_t)(blk * ACT_RT) * 8, ycol, a0, a1, h0, h1);
-          } else {
-            // block touches a segment end: exact replicate semantics inside [0, L), zero (= the conv's
-            // "same" padding of the ACTIVATED signal) outside
+          if (r0 + ACT_RT <= 0 || r0 >= L) {
+            // block entirely outside the segment: the conv's "same" zero padding of the ACTIVATED signal
 #pragma unroll 1
-            for (int tt = 0; tt < ACT_RT; ++tt) {
-              const int ts = r0 + tt;
-              float2 v = make_float2(0.f, 0.f);
-              if (ts >= 0 && ts < L) v = actcore::exact_clamped(rcol, tA0 - 5, rrows, ts, L, a0, a1, h0, h1);
-              actcore::stpair(ycol + tt * 8, v);
+            for (int tt = 0; tt < ACT_RT; ++tt) *reinterpret_cast<uint32_t*>(ycol + tt * 8) = 0u;
+          } else {
+            // the raw slab already carries the replicate padding of the input (producer), so the interior
+            // formulas hold everywhere except the three outputs next to each segment end, which see the
+            // replicate padding of the activated 2x signal: those are patched with the exact form
+            actcore::stream_packed<ACT_RT>(rcol + (size_t)(blk * ACT_RT) * 8, ycol, a0, a1, h0, h1);
+            if (r0 < 3 || r0 + ACT_RT > L - 3) {
+#pragma unroll 1
+              for (int tt = 0; tt < ACT_RT; ++tt) {
+                const int ts = r0 + tt;
+                if (ts < 0 || ts >= L) *reinterpret_cast<uint32_t*>(ycol + tt * 8) = 0u;
+                else if (ts < 3 || ts >= L - 3)
+                  actcore::stpair(ycol + tt * 8, actcore::exact_clamped(rcol, tA0 - 5, rrows, ts, L, a0, a1, h0, h1));
+              }
             }
           }
         }

@@ -186,3 +186,29 @@ def test_checkpoint_layout_gives_same_audio(gen, synth_sd):
     g2.eval()
     out = _run(g2, x, emb, "fp32")
     assert np.abs(out - ref).max() <= 1e-5
+
+
+def test_native_speaker_encoder_matches_reference_golden(gen, golden_dir):
+    """bvg_speaker_embedding (csrc/bvg_ecapa.cu) against the unmodified reference's ECAPA outputs,
+    without and with relative lengths (ECAPA_TDNN.py:543-581)."""
+    e = np.load(os.path.join(golden_dir, "ecapa.npz"))
+    emb = gen.speaker_embedding(torch.as_tensor(e["mel"]).cuda()).cpu().numpy()
+    assert emb.shape == e["emb"].shape
+    err = np.abs(emb - e["emb"]).max()
+    emb_l = gen.speaker_embedding(torch.as_tensor(e["mel"]).cuda(), torch.as_tensor(e["lens"])).cpu().numpy()
+    err_l = np.abs(emb_l - e["emb_lens"]).max()
+    print("native ECAPA max-abs", err, "with lens", err_l, "scale", np.abs(e["emb"]).max())
+    assert err <= 2e-4 and err_l <= 2e-4
+
+
+@pytest.mark.parametrize("B,Tm", [(1, 5), (3, 37), (2, 511)])
+def test_native_speaker_encoder_matches_oracle(gen, synth_sd, B, Tm):
+    """Short, ragged and prompt-sized mel inputs against the numpy oracle (fp64)."""
+    rng = np.random.default_rng(B * 1000 + Tm)
+    mel = (2.0 * rng.standard_normal((B, Tm, 100)) - 0.3).astype(np.float32)
+    lens = None if B == 1 else np.linspace(0.45, 1.0, B).astype(np.float32)
+    ref = O.ecapa_forward(mel, synth_sd, lengths=lens)
+    emb = gen.speaker_embedding(torch.as_tensor(mel).cuda(), None if lens is None else torch.as_tensor(lens)).cpu().numpy()
+    err = np.abs(emb - ref).max()
+    print("native ECAPA vs oracle", (B, Tm), err, "scale", np.abs(ref).max())
+    assert err <= 3e-4 * max(1.0, np.abs(ref).max())
