@@ -133,16 +133,21 @@ __device__ __forceinline__ u64 add2(u64 a, u64 b) {
 template <typename T, int RT, int WPB, bool PRECISE, bool PACKED>
 __global__ void __launch_bounds__(WPB * 32, sizeof(T) == 2 ? 2 : 1)
 act1d_c8_v3_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __restrict__ alpha,
-                   const float* __restrict__ inv_beta, const SegDesc* __restrict__ seg, int R) {
+                   const float* __restrict__ inv_beta, const SegDesc* __restrict__ seg, int R, int tiles, int nchunks) {
   constexpr int RS = RT + 11;   // region stride in rows: odd, >= RT + 10
   constexpr int NX = RT + 10;   // staged rows per region: r0-5 .. r0+RT+4
   extern __shared__ uint4 smem4[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tile = blockIdx.x * WPB + warp, chunk = blockIdx.y, b = blockIdx.z;
+  // work item = (8-channel chunk, tile of 8*RT rows) of one segment, flattened so that the warps of a
+  // block stay busy when a segment is only a few tiles long (the first stages: 940 rows = 4 tiles)
+  // (tiles == 0 selects the plain mapping blockIdx = (tile group, chunk, segment) used for long segments)
+  const int item = blockIdx.x * WPB + warp, b = blockIdx.z;
+  const int chunk = tiles ? item / tiles : (int)blockIdx.y, tile = tiles ? item - chunk * tiles : item;
+  if (chunk >= nchunks) return;   // warp-uniform; no block barrier is ever used
   const SegDesc sd = seg[b];
   const int L = sd.len;
   const int tile0 = tile * (8 * RT);
-  if (tile0 >= L) return;   // warp-uniform; no block barrier is ever used
+  if (tile0 >= L) return;
   T* region = reinterpret_cast<T*>(smem4) + (size_t)warp * (8 * RS * 8);
   const T* xb = x + ((size_t)chunk * R + sd.off) * 8;
 
@@ -290,14 +295,16 @@ act1d_c8_v3_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __re
 template <typename T, int RT, int WPB, bool PRECISE, bool PACKED = false>
 cudaError_t launch_v3(const ActArgs& a, cudaStream_t s) {
   const int tiles = (a.max_len + 8 * RT - 1) / (8 * RT);
-  dim3 grid((tiles + WPB - 1) / WPB, a.C / 8, a.B), block(WPB * 32);
+  const int nchunks = a.C / 8;
+  const bool flat = tiles < 4 * WPB;   // short segments: flatten (chunk, tile) so no warp of a block idles
+  dim3 grid(flat ? (tiles * nchunks + WPB - 1) / WPB : (tiles + WPB - 1) / WPB, flat ? 1 : nchunks, a.B), block(WPB * 32);
   const size_t smem = (size_t)WPB * 8 * (RT + 11) * 8 * sizeof(T);
   auto kern = act1d_c8_v3_kernel<T, RT, WPB, PRECISE, PACKED>;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
-  kern<<<grid, block, smem, s>>>((const T*)a.x, (T*)a.y, a.alpha, a.inv_beta, a.seg, a.R);
+  kern<<<grid, block, smem, s>>>((const T*)a.x, (T*)a.y, a.alpha, a.inv_beta, a.seg, a.R, flat ? tiles : 0, nchunks);
   return cudaGetLastError();
 }
 
