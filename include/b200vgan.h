@@ -117,6 +117,14 @@ int bvg_forward(bvg_handle* h, bvg_plan* plan, const void* latent, int32_t laten
                 const float* spk_emb, int32_t spk_batch, float* wav, void* workspace,
                 size_t workspace_bytes, void* stream);
 
+/* Same decode, but the final kernel also emits 16-bit PCM exactly as the reference's callers derive it from
+ * the waveform: clamp(32767 * wav, -32767, 32767) and a truncating cast (infer.py:462, :627, :650).
+ *   pcm [B, max_frames*hop] int16 (samples beyond a segment's length are 0);  wav_or_null: also write the
+ *   fp32 waveform (layout as in bvg_forward) when non-NULL.  Halves the device-to-host bytes of a dubbing job. */
+int bvg_forward_pcm16(bvg_handle* h, bvg_plan* plan, const void* latent, int32_t latent_dtype,
+                      const float* spk_emb, int32_t spk_batch, int16_t* pcm, float* wav_or_null,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
 /* Optional per-launch timing for roofline reports (bench.py): when enabled, bvg_forward brackets
  * every launch with a CUDA event pair on the caller's stream.  bvg_profile_read synchronises on
  * those events and returns, per kernel class (0 = standalone Activation1d, 1 = tcgen05 conv,

@@ -21,6 +21,7 @@ SYMBOLS = [
     "bvg_plan_num_launches", "bvg_forward", "bvg_forward_host", "bvg_activation1d", "bvg_conv1d",
     "bvg_conv_transpose1d", "bvg_workspace_reset", "bvg_profile_enable", "bvg_profile_read",
     "bvg_activation1d_packed", "bvg_act_conv1d", "bvg_ecapa_workspace_bytes", "bvg_speaker_embedding",
+    "bvg_forward_pcm16",
 ]
 
 
@@ -77,6 +78,7 @@ def load(rebuild: bool = False) -> C.CDLL:
     lib.bvg_profile_enable.argtypes = [vp, i32]
     lib.bvg_profile_read.argtypes = [vp, vp, vp, vp, vp]
     lib.bvg_forward.argtypes = [vp, vp, vp, i32, vp, i32, vp, vp, sz, vp]
+    lib.bvg_forward_pcm16.argtypes = [vp, vp, vp, i32, vp, i32, vp, vp, vp, sz, vp]
     lib.bvg_forward_host.argtypes = [vp, vp, vp, i32, vp, vp, i32, vp, vp, vp, sz, vp]
     lib.bvg_activation1d.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp]
     lib.bvg_activation1d_packed.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp]

@@ -222,9 +222,11 @@ class BigVGAN(nn.Module):
         return emb
 
     @torch.no_grad()
-    def forward_with_embedding(self, x, emb, x_lens: Optional[Sequence[int]] = None):
+    def forward_with_embedding(self, x, emb, x_lens: Optional[Sequence[int]] = None, pcm16: bool = False):
         """Decode with a precomputed speaker embedding.  `x_lens` (host ints, latent frames per
-        batch item) enables exact variable-length batches: item b is decoded as if alone."""
+        batch item) enables exact variable-length batches: item b is decoded as if alone.
+        `pcm16=True` returns int16 PCM [B, T*hop] instead of the fp32 waveform: the reference callers'
+        ``clamp(32767 * wav, -32767, 32767)`` + int16 cast (infer.py:462, :627, :650) fused into the last kernel."""
         if not x.is_cuda:
             raise _lib.BvgError("b200vgan has no CPU path: latents must live on a CUDA (sm_100) device")
         if x.dtype not in _DT:
@@ -244,8 +246,13 @@ class BigVGAN(nn.Module):
             mode = _lib.MODE_FP32 if self.precision == "fp32" else _lib.MODE_BF16
             plan = self._plan(frames, mode)
             ws = self._ensure_workspace(int(self._libh.bvg_plan_workspace_bytes(plan)), x.device)
-            wav = torch.empty(B, 1, T * self.hop, device=x.device, dtype=torch.float32)
             stream = torch.cuda.current_stream(x.device).cuda_stream
+            if pcm16:
+                pcm = torch.empty(B, T * self.hop, device=x.device, dtype=torch.int16)
+                _lib.check(self._libh.bvg_forward_pcm16(self._handle, plan, x.data_ptr(), _DT[x.dtype], emb.data_ptr(),
+                                                        emb.shape[0], pcm.data_ptr(), None, ws.data_ptr(), ws.numel(), stream))
+                return pcm
+            wav = torch.empty(B, 1, T * self.hop, device=x.device, dtype=torch.float32)
             _lib.check(self._libh.bvg_forward(self._handle, plan, x.data_ptr(), _DT[x.dtype], emb.data_ptr(),
                                               emb.shape[0], wav.data_ptr(), ws.data_ptr(), ws.numel(), stream))
         return wav

@@ -583,9 +583,25 @@ size_t bvg_plan_workspace_bytes(const bvg_plan* p) { return p ? p->ws_bytes : 0;
 int32_t bvg_plan_max_frames(const bvg_plan* p) { return p ? p->max_frames : 0; }
 int32_t bvg_plan_num_launches(const bvg_plan* p) { return p ? p->num_launches : 0; }
 
+static int forward_impl(bvg_handle* h, bvg_plan* p, const void* latent, int32_t latent_dtype, const float* spk_emb,
+                        int32_t spk_batch, float* wav, int16_t* pcm, void* workspace, size_t workspace_bytes, void* stream);
+
 int bvg_forward(bvg_handle* h, bvg_plan* p, const void* latent, int32_t latent_dtype, const float* spk_emb,
                 int32_t spk_batch, float* wav, void* workspace, size_t workspace_bytes, void* stream) {
-  if (!h || !p || !latent || !spk_emb || !wav || !workspace) return fail("bvg_forward: null argument");
+  if (!wav) return fail("bvg_forward: null argument");
+  return forward_impl(h, p, latent, latent_dtype, spk_emb, spk_batch, wav, nullptr, workspace, workspace_bytes, stream);
+}
+
+int bvg_forward_pcm16(bvg_handle* h, bvg_plan* p, const void* latent, int32_t latent_dtype, const float* spk_emb,
+                      int32_t spk_batch, int16_t* pcm, float* wav_or_null, void* workspace, size_t workspace_bytes,
+                      void* stream) {
+  if (!pcm) return fail("bvg_forward_pcm16: null argument");
+  return forward_impl(h, p, latent, latent_dtype, spk_emb, spk_batch, wav_or_null, pcm, workspace, workspace_bytes, stream);
+}
+
+static int forward_impl(bvg_handle* h, bvg_plan* p, const void* latent, int32_t latent_dtype, const float* spk_emb,
+                        int32_t spk_batch, float* wav, int16_t* pcm, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!h || !p || !latent || !spk_emb || !workspace) return fail("bvg_forward: null argument");
   if (!h->finalized) return fail("bvg_forward: call bvg_finalize first");
   if (p->h != h) return fail("bvg_forward: plan belongs to another handle");
   if (workspace_bytes < p->ws_bytes) return fail("bvg_forward: workspace too small (%zu < %zu)", workspace_bytes, p->ws_bytes);
@@ -658,7 +674,7 @@ int bvg_forward(bvg_handle* h, bvg_plan* p, const void* latent, int32_t latent_d
     const SegDesc* seg = p->seg_dev + (size_t)g * B;
     if (run_act(h->act_post, p, g, stage_in, ws + p->off_A[g], s)) return 1;
     ProfScope ps(h, s, PROF_OTHER, 0.0, ((double)p->C[g] * p->esize + 4.0) * (double)p->sumlen[g]);
-    CK(launch_conv_post_tanh(ws + p->off_A[g], dt, h->conv_post.w_raw, h->conv_post.bias, wav, seg, B, p->C[g], p->R[g],
+    CK(launch_conv_post_tanh(ws + p->off_A[g], dt, h->conv_post.w_raw, h->conv_post.bias, wav, (short*)pcm, seg, B, p->C[g], p->R[g],
                              p->max_frames * h->hop, s));
   }
   p->num_launches = h->launch_counter;   // what this forward actually issued (fused layers launch once)

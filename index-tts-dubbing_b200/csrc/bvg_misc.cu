@@ -71,8 +71,8 @@ __global__ void cond_bias_kernel(const float* __restrict__ bias, const float* __
 // conv_post (C -> 1, k = 7, pad 3) + tanh  (models.py:184, :247-248), C <= 64.  wav [B][Lmax] fp32.
 template <typename T>
 __global__ void conv_post_tanh_kernel(const T* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
-                                      float* __restrict__ wav, const SegDesc* __restrict__ seg, int C, int R,
-                                      int Lmax) {
+                                      float* __restrict__ wav, short* __restrict__ pcm, const SegDesc* __restrict__ seg,
+                                      int C, int R, int Lmax) {
   __shared__ float ws[7][64];
   for (int i = threadIdx.x; i < 7 * C; i += blockDim.x) {
     int j = i / C, c = i - j * C;
@@ -99,7 +99,10 @@ __global__ void conv_post_tanh_kernel(const T* __restrict__ x, const float* __re
     }
     out = tanhf(acc);
   }
-  wav[(size_t)b * Lmax + t] = out;
+  if (wav) wav[(size_t)b * Lmax + t] = out;
+  // 16-bit PCM as the reference's callers produce it: clamp(32767 * wav, -32767, 32767) then a truncating
+  // cast (infer.py:462, :627, :650)
+  if (pcm) pcm[(size_t)b * Lmax + t] = (short)__float2int_rz(fminf(fmaxf(__fmul_rn(32767.f, out), -32767.f), 32767.f));
 }
 
 // Conv1d weight [Cout][Cin][k] -> [k][Cin][Cout]
@@ -191,12 +194,12 @@ cudaError_t launch_cond_bias(const float* bias, const float* cw, const float* cb
   return cudaGetLastError();
 }
 
-cudaError_t launch_conv_post_tanh(const void* x, int dtype, const float* w, const float* bias, float* wav,
+cudaError_t launch_conv_post_tanh(const void* x, int dtype, const float* w, const float* bias, float* wav, short* pcm,
                                   const SegDesc* seg, int B, int C, int R, int Lmax, cudaStream_t s) {
   if (B <= 0 || Lmax <= 0) return cudaSuccess;
   dim3 g(nblk(Lmax, 256), B), blk(256);
-  if (dtype == 0) conv_post_tanh_kernel<float><<<g, blk, 0, s>>>((const float*)x, w, bias, wav, seg, C, R, Lmax);
-  else conv_post_tanh_kernel<__nv_bfloat16><<<g, blk, 0, s>>>((const __nv_bfloat16*)x, w, bias, wav, seg, C, R, Lmax);
+  if (dtype == 0) conv_post_tanh_kernel<float><<<g, blk, 0, s>>>((const float*)x, w, bias, wav, pcm, seg, C, R, Lmax);
+  else conv_post_tanh_kernel<__nv_bfloat16><<<g, blk, 0, s>>>((const __nv_bfloat16*)x, w, bias, wav, pcm, seg, C, R, Lmax);
   return cudaGetLastError();
 }
 

@@ -9,7 +9,7 @@ cudaError_t launch_c8_to_nct(const void* x, int in_dtype, float* y, const SegDes
                              cudaStream_t s);
 cudaError_t launch_cond_bias(const float* bias, const float* cw, const float* cb, const float* spk, float* out, int C,
                              int D, int B, int spkB, int out_bstride, cudaStream_t s);
-cudaError_t launch_conv_post_tanh(const void* x, int dtype, const float* w, const float* bias, float* wav,
+cudaError_t launch_conv_post_tanh(const void* x, int dtype, const float* w, const float* bias, float* wav, short* pcm,
                                   const SegDesc* seg, int B, int C, int R, int Lmax, cudaStream_t s);
 cudaError_t launch_repack_conv(const float* w, float* wp, int Cout, int Cin, int k, cudaStream_t s);
 cudaError_t launch_repack_convt(const float* w, float* wp, int Cin, int Cout, int k, int u, cudaStream_t s);

@@ -212,3 +212,18 @@ def test_native_speaker_encoder_matches_oracle(gen, synth_sd, B, Tm):
     err = np.abs(emb - ref).max()
     print("native ECAPA vs oracle", (B, Tm), err, "scale", np.abs(ref).max())
     assert err <= 3e-4 * max(1.0, np.abs(ref).max())
+
+
+def test_pcm16_output_matches_reference_postprocessing(gen):
+    """bvg_forward_pcm16 == the callers' clamp(32767*wav, -32767, 32767).type(int16) (infer.py:462, :650)."""
+    from b200vgan import synth
+    x = torch.as_tensor(synth.make_latents(5, 0, 2, 9)).cuda()
+    emb = torch.as_tensor(synth.make_speaker_embedding(B=1)).cuda()
+    for precision in ("fp32", "bf16"):
+        gen.precision = precision
+        wav = gen.forward_with_embedding(x, emb, x_lens=[9, 4])
+        pcm = gen.forward_with_embedding(x, emb, x_lens=[9, 4], pcm16=True)
+        ref = torch.clamp(32767 * wav.squeeze(1), -32767.0, 32767.0).type(torch.int16)
+        assert pcm.dtype == torch.int16 and tuple(pcm.shape) == (2, 9 * 1024)
+        assert torch.equal(pcm, ref)
+        assert int(pcm[1, 4 * 1024:].abs().max()) == 0
