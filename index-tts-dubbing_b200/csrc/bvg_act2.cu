@@ -130,8 +130,8 @@ __device__ __forceinline__ u64 add2(u64 a, u64 b) {
   return d;
 }
 
-template <typename T, int RT, int WPB, bool PRECISE, bool PACKED>
-__global__ void __launch_bounds__(WPB * 32, sizeof(T) == 2 ? 2 : 1)
+template <typename T, int RT, int WPB, bool PRECISE, bool PACKED, int MINB = (sizeof(T) == 2 ? 2 : 1)>
+__global__ void __launch_bounds__(WPB * 32, MINB)
 act1d_c8_v3_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __restrict__ alpha,
                    const float* __restrict__ inv_beta, const SegDesc* __restrict__ seg, int R, int tiles, int nchunks) {
   constexpr int RS = RT + 11;   // region stride in rows: odd, >= RT + 10
@@ -292,14 +292,14 @@ act1d_c8_v3_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __re
   }
 }
 
-template <typename T, int RT, int WPB, bool PRECISE, bool PACKED = false>
+template <typename T, int RT, int WPB, bool PRECISE, bool PACKED = false, int MINB = (sizeof(T) == 2 ? 2 : 1)>
 cudaError_t launch_v3(const ActArgs& a, cudaStream_t s) {
   const int tiles = (a.max_len + 8 * RT - 1) / (8 * RT);
   const int nchunks = a.C / 8;
   const bool flat = tiles < 4 * WPB;   // short segments: flatten (chunk, tile) so no warp of a block idles
   dim3 grid(flat ? (tiles * nchunks + WPB - 1) / WPB : (tiles + WPB - 1) / WPB, flat ? 1 : nchunks, a.B), block(WPB * 32);
   const size_t smem = (size_t)WPB * 8 * (RT + 11) * 8 * sizeof(T);
-  auto kern = act1d_c8_v3_kernel<T, RT, WPB, PRECISE, PACKED>;
+  auto kern = act1d_c8_v3_kernel<T, RT, WPB, PRECISE, PACKED, MINB>;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -318,6 +318,15 @@ cudaError_t launch_act_c8_v2(const ActArgs& a, int dtype, bool precise, int rt, 
   if (precise) return launch_v3<__nv_bfloat16, 16, 8, true>(a, s);
   static const int packed = [] { const char* e = getenv("BVG_ACT_PACKED"); return e ? atoi(e) : 1; }();
   if (packed) {
+    // warps per block x resident blocks -> registers per thread.  Measured on cfg2 (round 1): 4 warps x 6
+    // blocks (24 warps/SM at 80 registers, 24 bytes of spill) beats 8 x 2 (16 warps at 128 registers) by
+    // 6 % overall -- smaller blocks fill the SMs better on the short early stages; the long stages sit on
+    // the FP32-pipe plateau either way.  BVG_ACT_OCC selects the other variants for experiments.
+    static const int occ = [] { const char* e = getenv("BVG_ACT_OCC"); return e ? atoi(e) : 3; }();
+    if (rt == 32 && occ == 1) return launch_v3<__nv_bfloat16, 32, 6, false, true, 3>(a, s);   // 18 warps, <= 112 regs
+    if (rt == 32 && occ == 2) return launch_v3<__nv_bfloat16, 32, 5, false, true, 4>(a, s);   // 20 warps, <= 96 regs
+    if (rt == 32 && occ == 3) return launch_v3<__nv_bfloat16, 32, 4, false, true, 6>(a, s);   // 24 warps, <= 80 regs
+    if (rt == 32 && occ == 4) return launch_v3<__nv_bfloat16, 32, 4, false, true, 5>(a, s);   // 20 warps, <= 96 regs
     if (rt == 16) return launch_v3<__nv_bfloat16, 16, 8, false, true>(a, s);
     if (rt == 24) return launch_v3<__nv_bfloat16, 24, 8, false, true>(a, s);
     return launch_v3<__nv_bfloat16, 32, 8, false, true>(a, s);
