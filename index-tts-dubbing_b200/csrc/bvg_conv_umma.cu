@@ -443,8 +443,9 @@ __global__ void __launch_bounds__(FUSE ? NTHREADS_FUSED : NTHREADS, 1) conv_umma
       uint32_t* tapshift = reinterpret_cast<uint32_t*>(tmem_slot + 2);   // [ntaps + 1] row shifts (16-byte units)
       for (int tp = 0; tp < a.ntaps; ++tp) tapshift[tp] = (uint32_t)(a.tap_off[tp] - ka.minoff);
       tapshift[a.ntaps] = 0;
-      auto run = [&](auto ms_tag) {
+      auto run = [&](auto ms_tag, auto nk_tag) {
         constexpr int MS = decltype(ms_tag)::value;
+        constexpr int NK = decltype(nk_tag)::value;   // K-steps per tap known at compile time (0 = runtime loop)
         // instruction descriptor: D=f32, A=B=bf16, both K-major, N=BN, M=128
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(ka.BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         const uint32_t lbo_a = (uint32_t)ka.astride * 16, lbo_b = (uint32_t)ka.BN * 16;
@@ -492,8 +493,7 @@ __global__ void __launch_bounds__(FUSE ? NTHREADS_FUSED : NTHREADS, 1) conv_umma
               }
               uint32_t alo = a_lo_stage + sh, blo = b_lo;
               uint32_t af = accum;
-#pragma unroll 2
-              for (int k16 = 0; k16 < nk16; ++k16) {
+              auto kstep = [&]() {
                 const uint64_t bd = ((uint64_t)b_hi << 32) | blo;
                 umma_bf16(d0, ((uint64_t)a_hi << 32) | alo, bd, idesc, af);
                 if (MS >= 2) umma_bf16(d0 + bnc, ((uint64_t)a_hi << 32) | (alo + 128u), bd, idesc, af);   // +128 rows
@@ -503,6 +503,13 @@ __global__ void __launch_bounds__(FUSE ? NTHREADS_FUSED : NTHREADS, 1) conv_umma
                 }
                 alo += a_kstep; blo += b_kstep;
                 af = 1;
+              };
+              if constexpr (NK > 0) {   // straight-line: no loop control between the MMAs of a tap
+#pragma unroll
+                for (int k16 = 0; k16 < NK; ++k16) kstep();
+              } else {
+#pragma unroll 2
+                for (int k16 = 0; k16 < nk16; ++k16) kstep();
               }
               accum = 1;
               if (!resident) umma_commit(B_EMPTY(sb));
@@ -520,9 +527,17 @@ __global__ void __launch_bounds__(FUSE ? NTHREADS_FUSED : NTHREADS, 1) conv_umma
           first = false;
         }
       };
-      if (ka.MSUB == 4) run(std::integral_constant<int, 4>{});
-      else if (ka.MSUB == 2) run(std::integral_constant<int, 2>{});
-      else run(std::integral_constant<int, 1>{});
+      // specialised (MSUB, K-steps) pairs = the narrow AMP-block layers, where the issue loop is the limit
+      using std::integral_constant;
+      const int nk = (ka.debug & 2) ? -1 : ka.KC / 2;
+      if (ka.MSUB == 4 && nk == 2) run(integral_constant<int, 4>{}, integral_constant<int, 2>{});        // C = 24
+      else if (ka.MSUB == 4 && nk == 3) run(integral_constant<int, 4>{}, integral_constant<int, 3>{});   // C = 48
+      else if (ka.MSUB == 2 && nk == 6) run(integral_constant<int, 2>{}, integral_constant<int, 6>{});   // C = 96
+      else if (ka.MSUB == 1 && nk == 4) run(integral_constant<int, 1>{}, integral_constant<int, 4>{});   // C >= 192 (KC = 8)
+      else if (ka.MSUB == 2 && nk == 4) run(integral_constant<int, 2>{}, integral_constant<int, 4>{});
+      else if (ka.MSUB == 4) run(integral_constant<int, 4>{}, integral_constant<int, 0>{});
+      else if (ka.MSUB == 2) run(integral_constant<int, 2>{}, integral_constant<int, 0>{});
+      else run(integral_constant<int, 1>{}, integral_constant<int, 0>{});
     }
     __syncwarp();
   } else if (warp < 2 + epiw) {
