@@ -187,6 +187,7 @@ ConvArgs make_conv_args(const ConvLayer& L, const bvg_plan* p, int gin, int gout
   a.x = x; a.y = y; a.res = res;
   a.w = umma ? (const void*)L.w_umma : (const void*)L.w_tap;
   a.bias = bias; a.bias_bstride = bias_bstride;
+  a.acc_img_scale = (float)p->h->nk;
   a.seg_in = p->seg_dev + (size_t)gin * p->B;
   a.seg_out = p->seg_dev + (size_t)gout * p->B;
   a.Rx = p->R[gin]; a.Ry = p->R[gout];
@@ -416,7 +417,7 @@ static int finalize_conv(bvg_handle* h, ConvLayer& L, cudaStream_t s, bool want_
       if (!L.w_umma) {
         if (dev_alloc(h, &L.w_umma, bytes)) return 1;
       }
-      CK(launch_repack_umma(L.w_tap, L.w_umma, L.ntaps, L.Cin, L.N, s));
+      CK(launch_repack_umma(L.w_tap, L.w_umma, L.ntaps, L.Cin, L.N, (float)h->nk, s));
     }
   }
   return 0;
@@ -795,7 +796,7 @@ int conv_op(bool transposed, const float* x, const float* w, const float* bias, 
   if (transposed) CK(launch_repack_convt(w, wt, Cin, Cout, k, u, s));
   else CK(launch_repack_conv(w, wt, Cout, Cin, k, s));
   ConvArgs a{};
-  a.x = xc; a.y = yc; a.res = rc; a.w = wt; a.bias = bias; a.bias_bstride = 0;
+  a.x = xc; a.y = yc; a.res = rc; a.w = wt; a.bias = bias; a.bias_bstride = 0; a.acc_img_scale = 1.f;
   a.seg_in = seg_dev; a.seg_out = seg_dev + B; a.Rx = Rin; a.Ry = Rout;
   a.Cin = Cin; a.Cout = Cout; a.ntaps = L.ntaps;
   for (int j = 0; j < L.ntaps; ++j) a.tap_off[j] = L.tap_off[j];
@@ -832,7 +833,7 @@ int conv_op(bool transposed, const float* x, const float* w, const float* bias, 
     size_t bytes = umma_weight_image_bytes(L.ntaps, Cin, L.N);
     if (!bytes || !conv_umma_supported(a)) return fail("conv op: shape not supported by the tcgen05 kernel");
     if (tmp.alloc(&wu, bytes)) return 1;
-    CK(launch_repack_umma(wt, wu, L.ntaps, Cin, L.N, s));
+    CK(launch_repack_umma(wt, wu, L.ntaps, Cin, L.N, 1.f, s));
     a.w = wu;
     CK(launch_conv_umma(a, s));
   } else {

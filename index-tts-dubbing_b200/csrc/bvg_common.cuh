@@ -36,6 +36,7 @@ struct ConvArgs {
   const SegDesc* seg_in;
   const SegDesc* seg_out;
   int bias_bstride;
+  float acc_img_scale;  // value on the diagonal of the weight image's second identity set (0 if unknown)
   int Rx, Ry;
   int Cin, Cout;        // Cout = channels of y; GEMM N = u * Cout
   int ntaps;

@@ -234,6 +234,9 @@ struct UmmaKernelArgs {
   // tile as A operand against identity weight images (appended to the layer's image), so the epilogue
   // issues no global loads (narrow stages were bound by that latency chain)
   int res_mma;
+  // same trick for `accumulate` (y = old + ...): the old output tile x (1/out_scale) * identity (second image set)
+  int acc_mma;
+  int n_extra;              // res_mma + acc_mma: extra k-block groups after the convolution's
   unsigned long long* trace;   // optional event trace of CTA 0 (BVG_CONV_TRACE), nullptr normally
   int debug;                // tuning aid (BVG_CONV_DEBUG): 1 = epilogue skips global memory, 2 = no MMAs, 4 = no A loads
 };
@@ -405,22 +408,25 @@ __global__ void __launch_bounds__(FUSE ? NTHREADS_FUSED : NTHREADS, 1) conv_umma
             }
           }
         }
-        if (ka.res_mma) {
-          // residual k-blocks: the tile's TM output rows of `res`, placed at slab row -minoff
+        for (int e = 0; e < ka.n_extra; ++e) {
+          // residual / old-output k-blocks: the tile's TM output rows of the source, placed at slab row -minoff
+          const bool is_old = ka.acc_mma && e == ka.n_extra - 1;
+          const __nv_bfloat16* srcg = is_old ? reinterpret_cast<const __nv_bfloat16*>(a.y) : resg;
+          const int img_set = is_old ? 1 : 0;
           for (int kb = 0; kb < ka.NKB; ++kb) {
             const int kcl = (kb == ka.NKB - 1) ? ka.kc_last_load : ka.KC;
             mbar_wait(A_EMPTY(sa), pa ^ 1);
             mbar_expect_tx(AR_FULL(sa), (uint32_t)(kcl * TM * 16));
             const uint32_t adst = smem_u32(a_smem + (size_t)sa * ka.a_stage_bytes) - (uint32_t)(ka.minoff * 16);
             for (int c = 0; c < kcl; ++c) {
-              const __nv_bfloat16* src = resg + ((size_t)(kb * ka.KC + c) * a.Ry + rrow0c) * 8;
+              const __nv_bfloat16* src = srcg + ((size_t)(kb * ka.KC + c) * a.Ry + rrow0c) * 8;
               bulk_g2s(adst + (uint32_t)(c * ka.astride) * 16, src, (uint32_t)(TM * 16), AR_FULL(sa));
             }
             if (++sa == ka.NA) { sa = 0; pa ^= 1; }
             if (!ka.b_resident || first) {
               if (!ka.b_resident) mbar_wait(B_EMPTY(sb), pb ^ 1);
               mbar_expect_tx(B_FULL(sb), (uint32_t)ka.b_stage_bytes);
-              const uint8_t* src = wimg + ((size_t)ka.NKB * a.ntaps + kb) * ka.b_stage_bytes;   // identity images (NT == 1)
+              const uint8_t* src = wimg + ((size_t)ka.NKB * (a.ntaps + img_set) + kb) * ka.b_stage_bytes;   // identity images (NT == 1)
               bulk_g2s(smem_u32(b_smem + (size_t)sb * ka.b_stage_bytes), src, (uint32_t)ka.b_stage_bytes, B_FULL(sb));
               if (++sb == ka.NB) { sb = 0; pb ^= 1; }
             }
@@ -464,7 +470,7 @@ __global__ void __launch_bounds__(FUSE ? NTHREADS_FUSED : NTHREADS, 1) conv_umma
         int sa = 0, pa = 0, sb = 0, pb = 0, acc = 0, pacc = 0;
         uint32_t a_lo_stage = a_lo0, b_lo = b_lo0;
         uint32_t ph_act = 0, ph_res = 0;   // fused mode: per-stage phase bits of A_FULL / AR_FULL
-        const int nkbt = ka.res_mma ? 2 * NKB : NKB;
+        const int nkbt = (1 + ka.n_extra) * NKB;
         bool first = true;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
           TRACE(1, 0, t);
@@ -552,7 +558,8 @@ __global__ void __launch_bounds__(FUSE ? NTHREADS_FUSED : NTHREADS, 1) conv_umma
     const bool plain = a.u == 1;
     __nv_bfloat16* yg = reinterpret_cast<__nv_bfloat16*>(a.y);
     const __nv_bfloat16* rg = ka.res_mma ? nullptr : reinterpret_cast<const __nv_bfloat16*>(a.res);
-    const bool simple = plain && use_sbias && rg == nullptr && !a.accumulate;
+    const bool accum_epi = a.accumulate && !ka.acc_mma;   // old output still to be added by the epilogue
+    const bool simple = plain && use_sbias && rg == nullptr && !accum_epi;
     const size_t cs = (size_t)a.Ry * 8;      // elements between consecutive 8-channel chunks
     int acc = 0, pacc = 0;
     int t = blockIdx.x;
@@ -630,7 +637,7 @@ __global__ void __launch_bounds__(FUSE ? NTHREADS_FUSED : NTHREADS, 1) conv_umma
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             if (rg && ok[u]) resv[u] = *reinterpret_cast<const uint4*>(rg + base + u * cs);
-            if (a.accumulate && ok[u]) oldv[u] = *reinterpret_cast<const uint4*>(yg + base + u * cs);
+            if (accum_epi && ok[u]) oldv[u] = *reinterpret_cast<const uint4*>(yg + base + u * cs);
           }
           tmem_ld_wait();
 #pragma unroll
@@ -643,7 +650,7 @@ __global__ void __launch_bounds__(FUSE ? NTHREADS_FUSED : NTHREADS, 1) conv_umma
             if (rg && ok[u]) unpack_add(resv[u], v);
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[j] *= a.out_scale;
-            if (a.accumulate && ok[u]) unpack_add(oldv[u], v);
+            if (accum_epi && ok[u]) unpack_add(oldv[u], v);
             if (ok[u]) *reinterpret_cast<uint4*>(yg + base + u * cs) = pack8(v);
           }
         } else {
@@ -669,7 +676,7 @@ __global__ void __launch_bounds__(FUSE ? NTHREADS_FUSED : NTHREADS, 1) conv_umma
             if (rg) { const uint4 p = *reinterpret_cast<const uint4*>(rg + off); unpack_add(p, v); }
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[j] *= a.out_scale;
-            if (a.accumulate) { const uint4 p = *reinterpret_cast<const uint4*>(yg + off); unpack_add(p, v); }
+            if (accum_epi) { const uint4 p = *reinterpret_cast<const uint4*>(yg + off); unpack_add(p, v); }
             *reinterpret_cast<uint4*>(yg + off) = pack8(v);
           }
         }
@@ -747,9 +754,8 @@ __global__ void __launch_bounds__(FUSE ? NTHREADS_FUSED : NTHREADS, 1) conv_umma
         if (++sr == ka.NR) { sr = 0; pr ^= 1; }
         if (++sa == ka.NA) { sa = 0; pa ^= 1; }
       }
-      if (ka.res_mma)   // the residual k-blocks use the next NKB stages of the A ring
-        for (int kb = 0; kb < ka.NKB; ++kb)
-          if (++sa == ka.NA) { sa = 0; pa ^= 1; }
+      for (int kb = 0; kb < ka.n_extra * ka.NKB; ++kb)   // the residual / old-output k-blocks use the next stages of the A ring
+        if (++sa == ka.NA) { sa = 0; pa ^= 1; }
       t = tn;
     }
   }
@@ -790,7 +796,7 @@ __global__ void repack_umma_kernel(const float* __restrict__ wt, __nv_bfloat16* 
 }
 
 // identity images [kb][chunk KC][n BN][8] appended after the conv images of a square (Cin == N), single-n-tile layer
-__global__ void identity_umma_kernel(__nv_bfloat16* __restrict__ img, int N, int KC, int NKB, int BN) {
+__global__ void identity_umma_kernel(__nv_bfloat16* __restrict__ img, int N, int KC, int NKB, int BN, float value) {
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t total = (size_t)NKB * KC * BN * 8;
   if (idx >= total) return;
@@ -800,7 +806,7 @@ __global__ void identity_umma_kernel(__nv_bfloat16* __restrict__ img, int N, int
   int c = r % KC;
   int kb = r / KC;
   int ci = (kb * KC + c) * 8 + e;
-  img[idx] = __float2bfloat16_rn((ci == nn && nn < N) ? 1.f : 0.f);
+  img[idx] = __float2bfloat16_rn((ci == nn && nn < N) ? value : 0.f);
 }
 
 bool has_identity(const UmmaTiling& t, int Cin, int N) { return t.ok && t.NT == 1 && Cin == N; }
@@ -808,6 +814,12 @@ bool has_identity(const UmmaTiling& t, int Cin, int N) { return t.ok && t.NT == 
 bool use_res_mma(const ConvArgs& a, const UmmaTiling& t) {
   static const int maxc = env_int("BVG_RES_MMA_MAXC", 96);
   return a.res && a.u == 1 && has_identity(t, a.Cin, a.Cout) && a.Cin <= maxc;
+}
+// the second identity set holds acc_img_scale * I; usable when out_scale * acc_img_scale == 1
+bool use_acc_mma(const ConvArgs& a, const UmmaTiling& t) {
+  static const int maxc = env_int("BVG_RES_MMA_MAXC", 96);
+  const float p = a.out_scale * a.acc_img_scale;
+  return a.accumulate && a.u == 1 && has_identity(t, a.Cin, a.Cout) && a.Cin <= maxc && p > 0.999999f && p < 1.000001f;
 }
 
 void tap_range(const ConvArgs& a, int& mn, int& mx) {
@@ -840,8 +852,10 @@ bool configure(const ConvArgs& a, int msub, UmmaKernelArgs& ka, size_t& smem_byt
   ka.debug = debug_env;
   ka.trace = nullptr;
   ka.res_mma = use_res_mma(a, t) ? 1 : 0;
+  ka.acc_mma = use_acc_mma(a, t) ? 1 : 0;
+  ka.n_extra = ka.res_mma + ka.acc_mma;
   // pipeline depths within the smem budget
-  const int total_b = t.NKB * (a.ntaps + ka.res_mma);
+  const int total_b = t.NKB * (a.ntaps + ka.n_extra);
   ka.NA = t.NKB > 1 ? 2 : 3;
   ka.b_resident = 0;
   static const int allow_resident = env_int("BVG_CONV_RESIDENT", 1);
@@ -898,8 +912,10 @@ bool configure_fused(const ConvArgs& a, int msub, UmmaKernelArgs& ka, size_t& sm
   ka.act_alpha = a.act_alpha; ka.act_inv_beta = a.act_inv_beta;
   ka.NA = 2; ka.NR = 2;
   ka.res_mma = use_res_mma(a, t) ? 1 : 0;
+  ka.acc_mma = use_acc_mma(a, t) ? 1 : 0;
+  ka.n_extra = ka.res_mma + ka.acc_mma;
   const size_t fixed = (size_t)ka.NA * ka.a_stage_bytes + (size_t)ka.NR * ka.r_stage_bytes;
-  const int total_b = t.NKB * (a.ntaps + ka.res_mma);
+  const int total_b = t.NKB * (a.ntaps + ka.n_extra);
   ka.b_resident = 0;
   if (fixed + (size_t)ka.b_stage_bytes > (size_t)SMEM_BUDGET) return false;
   if (total_b <= MAX_STAGES && fixed + (size_t)total_b * ka.b_stage_bytes <= (size_t)SMEM_BUDGET) {
@@ -922,10 +938,10 @@ bool configure_fused(const ConvArgs& a, int msub, UmmaKernelArgs& ka, size_t& sm
 size_t umma_weight_image_bytes(int ntaps, int Cin, int N) {
   UmmaTiling t = make_tiling(ntaps, Cin, N);
   if (!t.ok) return 0;
-  return (size_t)(t.NT * t.NKB * ntaps + (has_identity(t, Cin, N) ? t.NKB : 0)) * t.KC * t.BN * 16;
+  return (size_t)(t.NT * t.NKB * ntaps + (has_identity(t, Cin, N) ? 2 * t.NKB : 0)) * t.KC * t.BN * 16;
 }
 
-cudaError_t launch_repack_umma(const float* wp_tap_major, void* img, int ntaps, int Cin, int N, cudaStream_t s) {
+cudaError_t launch_repack_umma(const float* wp_tap_major, void* img, int ntaps, int Cin, int N, float acc_img_scale, cudaStream_t s) {
   UmmaTiling t = make_tiling(ntaps, Cin, N);
   if (!t.ok) return cudaErrorInvalidValue;
   size_t total = (size_t)t.NT * t.NKB * ntaps * t.KC * t.BN * 8;
@@ -933,7 +949,10 @@ cudaError_t launch_repack_umma(const float* wp_tap_major, void* img, int ntaps, 
                                                                     t.KC, t.NKB, t.BN, t.NT);
   if (has_identity(t, Cin, N)) {
     const size_t itotal = (size_t)t.NKB * t.KC * t.BN * 8;
-    identity_umma_kernel<<<(unsigned)((itotal + 255) / 256), 256, 0, s>>>((__nv_bfloat16*)img + total, N, t.KC, t.NKB, t.BN);
+    // set 0: I (residual), set 1: acc_img_scale * I (old output of an accumulating layer; exact for small integers)
+    identity_umma_kernel<<<(unsigned)((itotal + 255) / 256), 256, 0, s>>>((__nv_bfloat16*)img + total, N, t.KC, t.NKB, t.BN, 1.f);
+    identity_umma_kernel<<<(unsigned)((itotal + 255) / 256), 256, 0, s>>>((__nv_bfloat16*)img + total + itotal, N, t.KC, t.NKB, t.BN,
+                                                                        acc_img_scale);
   }
   return cudaGetLastError();
 }
@@ -1006,7 +1025,9 @@ cudaError_t launch_conv_umma(const ConvArgs& a, cudaStream_t s) {
   static const int trace_cin = env_int("BVG_CONV_TRACE", 0);   // e.g. 24: trace the first k=3 conv with Cin == 24
   static bool traced = false;
   static const int trace_taps = env_int("BVG_CONV_TRACE_TAPS", 3);
-  const bool do_trace = trace_cin > 0 && !traced && a.Cin == trace_cin && a.u == 1 && a.ntaps == trace_taps;
+  static const int trace_res = env_int("BVG_CONV_TRACE_RES", 0);   // 1: trace a layer with a residual input
+  const bool do_trace = trace_cin > 0 && !traced && a.Cin == trace_cin && a.u == 1 && a.ntaps == trace_taps &&
+                        (a.res != nullptr) == (trace_res != 0);
   if (do_trace) {
     cudaMalloc((void**)&ka.trace, (4 + 4 * 1024) * 8);
     cudaMemset(ka.trace, 0, (4 + 4 * 1024) * 8);

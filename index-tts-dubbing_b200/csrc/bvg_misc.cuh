@@ -17,5 +17,5 @@ cudaError_t launch_snake_params(const float* la, const float* lb, float* alpha, 
                                 cudaStream_t s);
 // bf16 UMMA weight images (bvg_conv_umma.cu)
 size_t umma_weight_image_bytes(int ntaps, int Cin, int N);
-cudaError_t launch_repack_umma(const float* wp_tap_major, void* img, int ntaps, int Cin, int N, cudaStream_t s);
+cudaError_t launch_repack_umma(const float* wp_tap_major, void* img, int ntaps, int Cin, int N, float acc_img_scale, cudaStream_t s);
 cudaError_t launch_zero_guards(void* buf, int esize, const SegDesc* seg, int B, int C, int R, cudaStream_t s);
