@@ -602,14 +602,26 @@ __global__ void __launch_bounds__(FUSE ? NTHREADS_FUSED : NTHREADS, 1) conv_umma
           for (int j = 0; j < 8; ++j) bv[j] = sb4[j];
           const float osc = a.out_scale;
           tmem_ld_wait();
+          if (osc == 1.f) {   // the common case: no scaling pass
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            float v[8];
-            v[0] = (__uint_as_float(r[8 * u + 0]) + bv[2 * u].x) * osc; v[1] = (__uint_as_float(r[8 * u + 1]) + bv[2 * u].y) * osc;
-            v[2] = (__uint_as_float(r[8 * u + 2]) + bv[2 * u].z) * osc; v[3] = (__uint_as_float(r[8 * u + 3]) + bv[2 * u].w) * osc;
-            v[4] = (__uint_as_float(r[8 * u + 4]) + bv[2 * u + 1].x) * osc; v[5] = (__uint_as_float(r[8 * u + 5]) + bv[2 * u + 1].y) * osc;
-            v[6] = (__uint_as_float(r[8 * u + 6]) + bv[2 * u + 1].z) * osc; v[7] = (__uint_as_float(r[8 * u + 7]) + bv[2 * u + 1].w) * osc;
-            if (valid && nbase + 8 * u < N) *reinterpret_cast<uint4*>(yp + u * cs) = pack8(v);
+            for (int u = 0; u < 4; ++u) {
+              float v[8];
+              v[0] = __uint_as_float(r[8 * u + 0]) + bv[2 * u].x; v[1] = __uint_as_float(r[8 * u + 1]) + bv[2 * u].y;
+              v[2] = __uint_as_float(r[8 * u + 2]) + bv[2 * u].z; v[3] = __uint_as_float(r[8 * u + 3]) + bv[2 * u].w;
+              v[4] = __uint_as_float(r[8 * u + 4]) + bv[2 * u + 1].x; v[5] = __uint_as_float(r[8 * u + 5]) + bv[2 * u + 1].y;
+              v[6] = __uint_as_float(r[8 * u + 6]) + bv[2 * u + 1].z; v[7] = __uint_as_float(r[8 * u + 7]) + bv[2 * u + 1].w;
+              if (valid && nbase + 8 * u < N) *reinterpret_cast<uint4*>(yp + u * cs) = pack8(v);
+            }
+          } else {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              float v[8];
+              v[0] = (__uint_as_float(r[8 * u + 0]) + bv[2 * u].x) * osc; v[1] = (__uint_as_float(r[8 * u + 1]) + bv[2 * u].y) * osc;
+              v[2] = (__uint_as_float(r[8 * u + 2]) + bv[2 * u].z) * osc; v[3] = (__uint_as_float(r[8 * u + 3]) + bv[2 * u].w) * osc;
+              v[4] = (__uint_as_float(r[8 * u + 4]) + bv[2 * u + 1].x) * osc; v[5] = (__uint_as_float(r[8 * u + 5]) + bv[2 * u + 1].y) * osc;
+              v[6] = (__uint_as_float(r[8 * u + 6]) + bv[2 * u + 1].z) * osc; v[7] = (__uint_as_float(r[8 * u + 7]) + bv[2 * u + 1].w) * osc;
+              if (valid && nbase + 8 * u < N) *reinterpret_cast<uint4*>(yp + u * cs) = pack8(v);
+            }
           }
         } else if (plain) {
           // plain convolution: output row == q, column == channel; chunk c lives cs elements further.
@@ -654,30 +666,37 @@ __global__ void __launch_bounds__(FUSE ? NTHREADS_FUSED : NTHREADS, 1) conv_umma
             if (ok[u]) *reinterpret_cast<uint4*>(yg + base + u * cs) = pack8(v);
           }
         } else {
-          // transposed convolution: column n = (phase, channel), output row = q*u + phase - p
+          // transposed convolution: column n = (phase, channel), output row = q*u + phase - p.
+          // (phase, channel) of the four 8-column chunks advance incrementally (Cout is a multiple of 8);
+          // bias / residual / old rows are requested before waiting for the TMEM load.
+          int phase = nbase / a.Cout, co = nbase - phase * a.Cout;
+          bool ok[4];
+          size_t off[4];
+          float4 b0[4], b1[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int orow = q * a.u + phase - a.p;
+            ok[u] = qok && nbase + 8 * u < N && orow >= 0 && orow < soc.len;
+            off[u] = ((size_t)(co >> 3) * a.Ry + soc.off + orow) * 8;
+            b0[u] = b1[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (biasp && nbase + 8 * u < N) {
+              b0[u] = __ldg(reinterpret_cast<const float4*>(biasp + co));
+              b1[u] = __ldg(reinterpret_cast<const float4*>(biasp + co + 4));
+            }
+            co += 8;
+            if (co >= a.Cout) { co -= a.Cout; ++phase; }
+          }
           tmem_ld_wait();
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            const int n = nbase + 8 * u;
-            if (!(qok && n < N)) continue;
-            const int phase = n / a.Cout, co = n - phase * a.Cout;
-            const int orow = q * a.u + phase - a.p;
-            if (orow < 0 || orow >= soc.len) continue;
-            const size_t off = ((size_t)(co >> 3) * a.Ry + soc.off + orow) * 8;
             float v[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[8 * u + j]);
-            if (biasp) {
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(biasp + co));
-              const float4 b1 = __ldg(reinterpret_cast<const float4*>(biasp + co + 4));
-              v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-              v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-            }
-            if (rg) { const uint4 p = *reinterpret_cast<const uint4*>(rg + off); unpack_add(p, v); }
+            v[0] = __uint_as_float(r[8 * u + 0]) + b0[u].x; v[1] = __uint_as_float(r[8 * u + 1]) + b0[u].y;
+            v[2] = __uint_as_float(r[8 * u + 2]) + b0[u].z; v[3] = __uint_as_float(r[8 * u + 3]) + b0[u].w;
+            v[4] = __uint_as_float(r[8 * u + 4]) + b1[u].x; v[5] = __uint_as_float(r[8 * u + 5]) + b1[u].y;
+            v[6] = __uint_as_float(r[8 * u + 6]) + b1[u].z; v[7] = __uint_as_float(r[8 * u + 7]) + b1[u].w;
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[j] *= a.out_scale;
-            if (accum_epi) { const uint4 p = *reinterpret_cast<const uint4*>(yg + off); unpack_add(p, v); }
-            *reinterpret_cast<uint4*>(yg + off) = pack8(v);
+            if (ok[u]) *reinterpret_cast<uint4*>(yg + off[u]) = pack8(v);   // (no residual / accumulate for transposed layers)
           }
         }
       }
@@ -1002,6 +1021,7 @@ bool conv_umma_supported(const ConvArgs& a) {
   }
   UmmaKernelArgs ka{};
   size_t smem;
+  if (a.u != 1 && (a.res || a.accumulate)) return false;   // the transposed epilogue has no residual / accumulate path
   return a.tile_prefix != nullptr && (a.msub == 1 || a.msub == 2 || a.msub == 4) && configure(a, a.msub, ka, smem);
 }
 
