@@ -237,6 +237,15 @@ def run_ours(args):
             "launches_per_step": act["launches"] / args.steps, "ms_per_step": act["ms"] / args.steps,
             "share_of_step": act["ms"] / args.steps / step_ms_prof if step_ms_prof else None,
         }
+        # The activation is not HBM-bound: its real ceiling is the FP32 pipe (31 fp32 lane-operations per element:
+        # 12 up-FIR + 6 snake + 13 down-FIR; 128 FMA lanes per SM per clock, tools/fma_bench.cu).  Report that too.
+        sm_mhz = (clocks or {}).get("sm_mhz") or 0
+        if act["ms"] > 0 and sm_mhz:
+            elems = act["bytes"] / (2.0 * (2 if args.precision == "bf16" else 4))
+            fp32_tops = 31.0 * elems / (act["ms"] * 1e-3) / 1e12
+            fp32_peak = 148 * 128 * sm_mhz * 1e6 / 1e12
+            roofline_act["fp32_pipe"] = {"achieved_Tlaneops": fp32_tops, "peak_Tlaneops": fp32_peak, "frac": fp32_tops / fp32_peak,
+                                         "note": "31 fp32 lane-ops per element x elements / event time vs 148 SMs x 128 lanes x median SM clock"}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             frames = 47

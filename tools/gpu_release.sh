@@ -15,5 +15,7 @@ ncu --set full --clock-control none --import-source on -k regex:conv_umma -s 14 
     python tools/profile_step.py --iters 1 > gpurun_out/ncu_full_conv_$TAG.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:act1d -s 90 -c 1 -o gpurun_out/prof_act_s5_$TAG \
     python tools/profile_step.py --iters 1 > gpurun_out/ncu_full_act_$TAG.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:conv_umma -s 109 -c 1 -o gpurun_out/prof_conv_s5k11_$TAG \
+    python tools/profile_step.py --iters 1 > gpurun_out/ncu_full_conv5_$TAG.log 2>&1
 echo "ncu full rc=$?"
 head -c 1500 gpurun_out/bench_$TAG.json
