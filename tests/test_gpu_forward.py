@@ -227,3 +227,29 @@ def test_pcm16_output_matches_reference_postprocessing(gen):
         assert pcm.dtype == torch.int16 and tuple(pcm.shape) == (2, 9 * 1024)
         assert torch.equal(pcm, ref)
         assert int(pcm[1, 4 * 1024:].abs().max()) == 0
+
+
+@pytest.mark.parametrize("B,sec", [(64, 2.0), (32, 5.0), (2, 30.0)])
+def test_cfg5_sweep_corners_bf16_vs_fp32_mode(gen, B, sec):
+    """Corners of BASELINE.json config 5 (B in 1..64 x 2..30 s): many short and few long utterances.
+    Size-independent properties: bf16 path within its SNR bound of the fp32 path, and batch item i
+    identical to the same latents decoded alone (batch invariance)."""
+    from b200vgan import synth
+    T = synth.frames_for_seconds(sec)
+    x = synth.make_latents(5, B, B, T)
+    emb = synth.make_speaker_embedding(B=1)
+    ref = _run(gen, x, emb, "fp32")
+    wav = _run(gen, x, emb, "bf16")
+    assert wav.shape == (B, 1, T * 1024) and np.isfinite(wav).all()
+    snr = O.snr_db(ref, wav)
+    print("cfg5", (B, sec), "bf16-vs-fp32-mode SNR dB", snr)
+    assert snr >= BF16_SNR_DB
+    i = B - 1
+    alone = _run(gen, x[i:i + 1], emb, "bf16")
+    assert np.array_equal(alone[0], wav[i])
+
+
+def test_speaker_encoder_rejects_wrong_mel_width(gen):
+    from b200vgan import lib as L
+    with pytest.raises(L.BvgError):
+        gen.speaker_embedding(torch.zeros(1, 40, 80).cuda())
