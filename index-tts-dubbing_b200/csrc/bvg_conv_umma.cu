@@ -243,8 +243,8 @@ struct UmmaKernelArgs {
 
 struct TileRef { int nt, b, q0; };
 
-template <bool FUSE>
-__global__ void __launch_bounds__(FUSE ? NTHREADS_FUSED : NTHREADS, 1) conv_umma_kernel(const UmmaKernelArgs ka) {
+template <bool FUSE, int EPW = EPIW>
+__global__ void __launch_bounds__(FUSE ? NTHREADS_FUSED : 64 + 32 * EPW, 1) conv_umma_kernel(const UmmaKernelArgs ka) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const ConvArgs& a = ka.c;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(FUSE ? NTHREADS_FUSED : NTHREADS, 1) conv_umma
   // smem carve-up: [R stages (fused only)][A stages][B stages][barriers][tmem slot]
   uint8_t* r_smem = smem;
   uint8_t* a_smem = smem + (FUSE ? (size_t)ka.NR * ka.r_stage_bytes : 0);
-  constexpr int epiw = FUSE ? EPIW_FUSED : EPIW;
+  constexpr int epiw = FUSE ? EPIW_FUSED : EPW;
   uint8_t* b_smem = a_smem + (size_t)ka.NA * ka.a_stage_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(b_smem + (size_t)ka.NB * ka.b_stage_bytes);
   const uint32_t bar0 = smem_u32(bars);
@@ -1040,6 +1040,7 @@ cudaError_t launch_conv_umma(const ConvArgs& a, cudaStream_t s) {
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_umma_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX);
     if (e != cudaSuccess) { num_sms = 0; return e; }
   }
   static const int trace_cin = env_int("BVG_CONV_TRACE", 0);   // e.g. 24: trace the first k=3 conv with Cin == 24
@@ -1055,8 +1056,12 @@ cudaError_t launch_conv_umma(const ConvArgs& a, cudaStream_t s) {
     smem = SMEM_MAX;
   }
   const int total_tiles = ka.total_mt * ka.NT;
-  dim3 grid(total_tiles < num_sms ? total_tiles : num_sms), block(fuse ? NTHREADS_FUSED : NTHREADS);
+  // BVG_CONV_EPIW=4: 4 instead of 8 epilogue warps (192 threads, 32 K registers) -- leaves room for activation
+  // blocks of a concurrent stream on the same SM (co-scheduling experiment, tools/two_stream.py)
+  static const int epiw4 = env_int("BVG_CONV_EPIW", 8) == 4;
+  dim3 grid(total_tiles < num_sms ? total_tiles : num_sms), block(fuse ? NTHREADS_FUSED : (epiw4 ? 64 + 32 * 4 : NTHREADS));
   if (fuse) conv_umma_kernel<true><<<grid, block, smem, s>>>(ka);
+  else if (epiw4) conv_umma_kernel<false, 4><<<grid, block, smem, s>>>(ka);
   else conv_umma_kernel<false><<<grid, block, smem, s>>>(ka);
   if (do_trace) {
     cudaStreamSynchronize(s);

@@ -21,7 +21,7 @@ gs = [make(), make()]
 streams = [torch.cuda.Stream(), torch.cuda.Stream()]
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
-def run(nstream, B, steps=6, warm=3):
+def run(nstream, B, steps=6, warm=3, delay=0):
     xs = [torch.from_numpy(synth.make_latents(2, i, B, T)).cuda() for i in range(nstream)]
     times = []
     for it in range(warm + steps):
@@ -32,6 +32,8 @@ def run(nstream, B, steps=6, warm=3):
         for i in range(nstream):
             streams[i].wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(streams[i]):
+                if i == 1 and delay:
+                    torch.cuda._sleep(int(delay))   # phase offset: B's activations against A's convolutions
                 gs[i].forward_with_embedding(xs[i], emb)
         for i in range(nstream):
             torch.cuda.current_stream().wait_stream(streams[i])
@@ -41,6 +43,9 @@ def run(nstream, B, steps=6, warm=3):
             times.append(e0.elapsed_time(e1))
     ms = sum(times) / len(times)
     audio = nstream * B * T * 1024 / 24000
-    print(f"{nstream} stream(s) x B={B}: {ms:.2f} ms  -> {audio / ms * 1e3:.0f} audio-s/s", flush=True)
+    print(f"{nstream} stream(s) x B={B} delay {delay}: {ms:.2f} ms  -> {audio / ms * 1e3:.0f} audio-s/s", flush=True)
 
-run(1, 16); run(2, 8); run(2, 16); run(1, 8); run(1, 32)
+run(1, 16); run(2, 8)
+for d in (60000, 120000, 200000, 400000):
+    run(2, 8, delay=d)
+run(2, 16); run(2, 16, delay=150000)
