@@ -24,13 +24,26 @@
 // warps 2..9 = epilogue (TMEM lane quarter = warp_id % 4; the two warps of a quarter alternate over
 // the (sub-tile, 32-column group) work items).
 //
+// Residual / accumulate through the tensor core: for square layers with Cin <= 96 the residual tile
+// (and, for accumulating layers, the old output tile) is loaded as extra k-blocks and multiplied by
+// identity (resp. 1/out_scale * identity) weight images appended to the layer's image, so the epilogue
+// of those layers issues no global loads (see use_res_mma / use_acc_mma).
+//
+// conv_umma_kernel<true> (opt-in, BVG_FUSE_ACT=1) additionally computes Activation1d in 10 extra warps
+// between the producer (raw rows) and the MMA issuer (activated A operand); measured slower than the
+// separate activation pass in round 1, kept for the next round.
+//
 // What the measurements behind this structure were (tools/umma_bench.cu, profiles/r1_umma_*):
 //   * one M=128 MMA costs max(N/2, ~40..50) cycles when issued from uniform registers, but ~124 when
 //     its descriptors are built in a divergent single-lane region (R2UR per operand) -> the issuer is
 //     ONE thread chosen with elect.sync (ptxas then emits uniform-datapath code for the whole loop);
 //   * consecutive MMAs into the same accumulator serialise -> the sub-tile loop is innermost;
 //   * narrow stages are bound by per-tile fixed costs (barrier round trips, tile decode, epilogue
-//     latency), not by MMA or HBM -> big tiles (MSUB = 4), x32 TMEM loads, decode prefetch.
+//     latency), not by MMA or HBM -> big tiles (MSUB = 4), x32 TMEM loads, decode prefetch;
+//   * the tensor pipe queues only a few MMAs: every cycle the issuing thread spends between taps is
+//     idle pipe time (BVG_CONV_TRACE showed ~400 cycles per tap) -> incremental 32-bit descriptors and
+//     straight-line K-step sequences; tools/umma_bench2.cu gives the per-shape floor (46 cycles for
+//     M128 x N32 x K16: the A operand's shared-memory reads, not the math).
 #include <cstdio>
 #include <cstdlib>
 #include <type_traits>
