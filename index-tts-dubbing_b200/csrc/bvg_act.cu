@@ -138,6 +138,13 @@ cudaError_t launch_act_c8(const ActArgs& a, int dtype, bool precise, cudaStream_
   // and BVG_ACT_RT=16|32 the rows per thread (A/B knobs used while tuning on the GPU box).
   static const int use_v1 = [] { const char* e = getenv("BVG_ACT_V1"); return (e && e[0] == '1') ? 1 : 0; }();
   static const int rt = [] { const char* e = getenv("BVG_ACT_RT"); int v = e ? atoi(e) : 32; return (v == 16 || v == 24) ? v : 32; }();
+  // bf16 mode: version 4 (both FIRs on the tensor cores via warp-level MMA, bvg_act3.cu).  Measured on cfg2 (round 1):
+  // 11 % faster than the register-streamed kernel from 15 040 rows per segment on, equal at 3 760, 10 % slower at 940
+  // (coarser work items).  It is used for EVERY length so that a segment's samples do not depend on what else is in
+  // the batch (the two kernels round differently).  BVG_ACT_MMA=0 selects version 3; BVG_ACT_MMA_MINLEN a length threshold.
+  static const int use_mma = [] { const char* e = getenv("BVG_ACT_MMA"); return e ? atoi(e) : 1; }();
+  static const int mma_minlen = [] { const char* e = getenv("BVG_ACT_MMA_MINLEN"); return e ? atoi(e) : 1; }();
+  if (use_mma && dtype == 1 && !precise && a.max_len >= mma_minlen) return launch_act_c8_mma(a, s);
   if (!use_v1) return launch_act_c8_v2(a, dtype, precise, rt, s);
   dim3 grid((a.max_len + TR - 1) / TR, a.C / 8, a.B), block(NTHREADS);
   if (dtype == 0) {

@@ -99,7 +99,7 @@ __device__ __forceinline__ void stream_packed(const __nv_bfloat16* xr, __nv_bflo
 
 // Exact output at segment time t (0 <= t < L) with both replicate paddings (input and activated 2x
 // signal).  col0 points at this thread's channel pair in slab row 0; slab row r holds x[slab_t0 + r].
-__device__ __noinline__ float2 exact_clamped(const __nv_bfloat16* col0, int slab_t0, int slab_rows, int t, int L,
+static __device__ __noinline__ float2 exact_clamped(const __nv_bfloat16* col0, int slab_t0, int slab_rows, int t, int L,
                                              float a0, float a1, float h0, float h1) {
   const float taps[6] = {BVG_F0, BVG_F1, BVG_F2, BVG_F3, BVG_F4, BVG_F5};
   float accx = 0.f, accy = 0.f;
