@@ -232,20 +232,22 @@ def run_ours(args):
             "share_of_step": conv["ms"] / args.steps / step_ms_prof if step_ms_prof else None,
         }
         roofline_act = {
-            "bound": "hbm", "kernel": "act1d_c8_v3_kernel (fused Activation1d: up-FIR -> SnakeBeta -> down-FIR)", "achieved": act_gbs, "peak": pk["hbm_gbs"],
+            "bound": "hbm", "kernel": ("act1d_c8_mma_kernel (Activation1d: up-FIR and down-FIR as warp-level MMAs, SnakeBeta on CUDA cores)" if args.precision == "bf16" else "act1d_c8_v3_kernel (Activation1d, register-streamed fp32)"), "achieved": act_gbs, "peak": pk["hbm_gbs"],
             "unit": "GB/s", "frac": act_gbs / pk["hbm_gbs"], "traffic": None,
             "launches_per_step": act["launches"] / args.steps, "ms_per_step": act["ms"] / args.steps,
             "share_of_step": act["ms"] / args.steps / step_ms_prof if step_ms_prof else None,
         }
-        # The activation is not HBM-bound: its real ceiling is the FP32 pipe (31 fp32 lane-operations per element:
-        # 12 up-FIR + 6 snake + 13 down-FIR; 128 FMA lanes per SM per clock, tools/fma_bench.cu).  Report that too.
+        # The activation is not HBM-bound.  bf16 mode (act1d_c8_mma_kernel: FIRs on the tensor cores): the nearest hardware
+        # ceiling is the MUFU rate (2 cos per element, 16 lanes per SM per clock); fp32 mode (register-streamed kernel): the
+        # FP32 pipe (31 lane-operations per element, 128 lanes per SM per clock, tools/fma_bench.cu).  Report that ceiling too.
         sm_mhz = (clocks or {}).get("sm_mhz") or 0
         if act["ms"] > 0 and sm_mhz:
             elems = act["bytes"] / (2.0 * (2 if args.precision == "bf16" else 4))
-            fp32_tops = 31.0 * elems / (act["ms"] * 1e-3) / 1e12
-            fp32_peak = 148 * 128 * sm_mhz * 1e6 / 1e12
-            roofline_act["fp32_pipe"] = {"achieved_Tlaneops": fp32_tops, "peak_Tlaneops": fp32_peak, "frac": fp32_tops / fp32_peak,
-                                         "note": "31 fp32 lane-ops per element x elements / event time vs 148 SMs x 128 lanes x median SM clock"}
+            ops_per_elem, lanes, pipe = (2.0, 16, "mufu") if args.precision == "bf16" else (31.0, 128, "fp32")
+            ach = ops_per_elem * elems / (act["ms"] * 1e-3) / 1e12
+            peak = 148 * lanes * sm_mhz * 1e6 / 1e12
+            roofline_act["compute_pipe"] = {"pipe": pipe, "achieved_Tlaneops": ach, "peak_Tlaneops": peak, "frac": ach / peak,
+                                            "note": f"{ops_per_elem:g} {pipe} lane-ops per element x elements / event time vs 148 SMs x {lanes} lanes x median SM clock"}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             frames = 47

@@ -79,6 +79,7 @@ struct Stream {
   int chunk, tile0, L;        // 8-channel chunk, first output row, segment length (tile0 >= L: nothing to do)
 };
 
+template <bool UP_LO>   // UP_LO: add the bf16 rounding residual of the up-FIR taps (second MMA per column tile)
 __global__ void __launch_bounds__(WPB * 32, MINB)
 act1d_c8_mma_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, const float* __restrict__ alpha,
                     const float* __restrict__ inv_beta, const SegDesc* __restrict__ seg, int R, int ntiles, int nchunks,
@@ -183,7 +184,7 @@ act1d_c8_mma_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restri
     ldsm_x4_trans(ld_base + (uint32_t)(4 * j + 5) * 16, xa);   // input rows 4j-3 .. 4j+12 (region row = local time + 8)
     float c[4] = {0.f, 0.f, 0.f, 0.f};
     mma16816(c, xa, gup_hi[0], gup_hi[1]);
-    mma16816(c, xa, gup_lo[0], gup_lo[1]);
+    if (UP_LO) mma16816(c, xa, gup_lo[0], gup_lo[1]);
     const float s0 = fmaf(-hh[0], __cosf(a2[0] * c[0]), c[0]), s1 = fmaf(-hh[0], __cosf(a2[0] * c[1]), c[1]);
     const float s2 = fmaf(-hh[1], __cosf(a2[1] * c[2]), c[2]), s3 = fmaf(-hh[1], __cosf(a2[1] * c[3]), c[3]);
     p0 = pack_bf16(s0, s1);
@@ -251,11 +252,17 @@ cudaError_t launch_act_c8_mma(const ActArgs& a, cudaStream_t s) {
   const size_t smem = (size_t)WPB * 2 * XROWS * 16;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(act1d_c8_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(act1d_c8_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(act1d_c8_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
-  act1d_c8_mma_kernel<<<grid, block, smem, s>>>((const __nv_bfloat16*)a.x, (__nv_bfloat16*)a.y, a.alpha, a.inv_beta, a.seg, a.R, ntiles,
+  static const int up_lo = [] { const char* e = getenv("BVG_ACT_MMA_UPLO"); return e ? atoi(e) : 1; }();
+  if (!up_lo)
+    act1d_c8_mma_kernel<false><<<grid, block, smem, s>>>((const __nv_bfloat16*)a.x, (__nv_bfloat16*)a.y, a.alpha, a.inv_beta, a.seg, a.R,
+                                                        ntiles, nchunks, GT);
+  else
+  act1d_c8_mma_kernel<true><<<grid, block, smem, s>>>((const __nv_bfloat16*)a.x, (__nv_bfloat16*)a.y, a.alpha, a.inv_beta, a.seg, a.R, ntiles,
                                                nchunks, GT);
   return cudaGetLastError();
 }

@@ -13,7 +13,7 @@ echo "launch list rc=$?"
 python tools/profile_step.py --iters 1 > gpurun_out/plain2_$TAG.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:conv_umma -s 14 -c 1 -o gpurun_out/prof_conv_s0k11_$TAG \
     python tools/profile_step.py --iters 1 > gpurun_out/ncu_full_conv_$TAG.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:act1d -s 90 -c 1 -o gpurun_out/prof_act_s5_$TAG \
+ncu --set full --clock-control none --import-source on -k regex:act1d_c8 -s 90 -c 1 -o gpurun_out/prof_act_s5_$TAG \
     python tools/profile_step.py --iters 1 > gpurun_out/ncu_full_act_$TAG.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:conv_umma -s 109 -c 1 -o gpurun_out/prof_conv_s5k11_$TAG \
     python tools/profile_step.py --iters 1 > gpurun_out/ncu_full_conv5_$TAG.log 2>&1
