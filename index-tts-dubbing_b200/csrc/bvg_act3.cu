@@ -16,13 +16,16 @@
 // tiles IS the A fragment of one down-FIR K-step (same trick as P = softmax(S) in attention kernels),
 // so the 2x activated signal lives only in registers.  Operand movement: ldmatrix.trans turns the
 // staged [time][8 channels] rows into A fragments, stmatrix.trans writes the result rows back.
-// Taps are split hi + lo in bf16 for the up-FIR (exact to 2^-17); the activated samples and the
-// down-FIR taps are single bf16 values (the same 2^-9 rounding the stored tensors have anyway).
+// Taps are split hi + lo in bf16 for the up-FIR (exact to 2^-17; its A operand is the stored bf16 tensor);
+// the down-FIR runs in fp16 (activated samples and taps rounded to 11 bits: finer than the 8 bits the
+// stored result keeps anyway, and fp16's range is ample for activation magnitudes).
 //
 // Formulas:  u[m] = 2 sum_k f[k] x[(m+5-k)/2],  y[t] = sum_k f[k] s[2t+k-5], replicate
 // padding of the input (staged rows are clamped) and of the activated signal (the three outputs next to
 // each segment end are recomputed exactly, actcore::exact_clamped).
 #include <cstdlib>
+
+#include <cuda_fp16.h>
 
 #include "bvg_act_core.cuh"
 #include "bvg_common.cuh"
@@ -51,6 +54,15 @@ __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], 
   asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void mma16816_f16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
+  __half2 h = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
 }
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
@@ -109,10 +121,14 @@ act1d_c8_mma_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restri
   // ---- constants: tap fragments and this thread's two channel rows (stream 0 / stream 1, channel g) ----
   uint32_t gup_hi[2], gup_lo[2];                      // up-FIR:   B[k][n] = 2 f[n + 11 - 2k]
   tap_frag([](int k, int n) { return n + 11 - 2 * k; }, 2.f, g, t, gup_hi, gup_lo);
-  uint32_t fdn[3][2], fdn_lo[3][2];                   // down-FIR: B_d[k][n] = f[16 d + k - 2n + 5], d = -1, 0, +1
-  tap_frag([](int k, int n) { return k - 2 * n - 11; }, 1.f, g, t, fdn[0], fdn_lo[0]);
-  tap_frag([](int k, int n) { return k - 2 * n + 5; }, 1.f, g, t, fdn[1], fdn_lo[1]);
-  tap_frag([](int k, int n) { return k - 2 * n + 21; }, 1.f, g, t, fdn[2], fdn_lo[2]);
+  uint32_t fdn[3][2];                                 // down-FIR: B_d[k][n] = f[16 d + k - 2n + 5], d = -1, 0, +1, as fp16
+#pragma unroll
+  for (int d = 0; d < 3; ++d)
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int k0 = 2 * t + 8 * half, off = 16 * (d - 1) + 5 - 2 * g;
+      fdn[d][half] = pack_f16(tap(k0 + off), tap(k0 + 1 + off));
+    }
   float a2[2], hh[2];
 #pragma unroll
   for (int s = 0; s < 2; ++s) {
@@ -187,8 +203,8 @@ act1d_c8_mma_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restri
     if (UP_LO) mma16816(c, xa, gup_lo[0], gup_lo[1]);
     const float s0 = fmaf(-hh[0], __cosf(a2[0] * c[0]), c[0]), s1 = fmaf(-hh[0], __cosf(a2[0] * c[1]), c[1]);
     const float s2 = fmaf(-hh[1], __cosf(a2[1] * c[2]), c[2]), s3 = fmaf(-hh[1], __cosf(a2[1] * c[3]), c[3]);
-    p0 = pack_bf16(s0, s1);
-    p1 = pack_bf16(s2, s3);
+    p0 = pack_f16(s0, s1);   // fp16 keeps 11 bits of the activated sample (bf16: 8); its range is ample for activations
+    p1 = pack_f16(s2, s3);
   };
   uint32_t ap[4], ac[4], an[4];   // down-FIR A fragments of K-steps J-1, J, J+1 (16 activated samples each)
   ap[0] = ap[1] = 0u;             // samples -16 .. -9 are never used (zero taps): skip their column tile
@@ -201,9 +217,9 @@ act1d_c8_mma_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restri
     if (!last) up_tile(2 * J + 3, N[2], N[3]);
     else N[2] = N[3] = 0u;        // beyond the last sample any output of this tile needs
     float c[4] = {hh[0], hh[0], hh[1], hh[1]};
-    mma16816(c, P, fdn[0][0], fdn[0][1]);
-    mma16816(c, C, fdn[1][0], fdn[1][1]);
-    mma16816(c, N, fdn[2][0], fdn[2][1]);
+    mma16816_f16(c, P, fdn[0][0], fdn[0][1]);
+    mma16816_f16(c, C, fdn[1][0], fdn[1][1]);
+    mma16816_f16(c, N, fdn[2][0], fdn[2][1]);
     // the raw rows these outputs overwrite were consumed by the column tiles above
     stsm_x2_trans(st_base + (uint32_t)(8 * J) * 16, pack_bf16(c[0], c[1]), pack_bf16(c[2], c[3]));
   };
