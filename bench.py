@@ -44,6 +44,27 @@ def peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "src": "fallback"}
 
 
+def ncu_dram_bytes(path):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE captured launch of the dominant kernel (ncu --set full summary
+    committed under profiles/; a capture, not a live measurement -- the live numbers are the CUDA-event times)."""
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    total, found = 0.0, 0
+    try:
+        for ln in open(path):
+            ln = ln.strip()
+            for key in ("dram__bytes_read.sum [", "dram__bytes_write.sum ["):
+                if ln.startswith(key):
+                    u = ln[len(key):ln.index("]")]
+                    total += float(ln.split("=")[1].replace(",", "")) * unit.get(u, 1.0)
+                    found += 1
+    except OSError:
+        return {}
+    if found != 2:
+        return {}
+    return {"bytes": total, "source": "ncu --set full, one launch (stage 0, k=11 conv, 768 ch, 15040 rows: 59 MB algorithmic incl. 13 MB weights), "
+                                      + os.path.relpath(path, ROOT)}
+
+
 class ClockSampler(threading.Thread):
     """Samples nvidia-smi clocks / throttle reasons every 200 ms while the timed region runs."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -223,11 +244,12 @@ def run_ours(args):
         act = prof["activation1d"]
         act_gbs = act["bytes"] / (act["ms"] * 1e-3) / 1e9 if act["ms"] > 0 else 0.0
         step_ms_prof = sum(v["ms"] for v in prof.values()) / args.steps
+        ncu_traffic = ncu_dram_bytes(os.path.join(ROOT, "profiles", "r1_rc5_ncu_full_conv_s0k11.txt"))
         roofline = {
             "bound": "tensor", "kernel": "conv_umma_kernel (tcgen05 implicit-GEMM conv1d)" if tc else "conv_simt_kernel",
             "achieved": conv_tflops, "peak": peak_tf, "unit": "TFLOP/s", "frac": conv_tflops / peak_tf,
             "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({pk['src']})",
-            "traffic": None,   # per-launch DRAM bytes from ncu --set full are in profiles/ (captured per launch, not averaged)
+            "traffic": ncu_traffic.get("bytes"), "traffic_source": ncu_traffic.get("source"),
             "launches_per_step": conv["launches"] / args.steps, "ms_per_step": conv["ms"] / args.steps,
             "share_of_step": conv["ms"] / args.steps / step_ms_prof if step_ms_prof else None,
         }
