@@ -277,3 +277,19 @@ def test_forward_is_cuda_graph_capturable(gen):
     eager1 = gen.forward_with_embedding(x_new, emb, x_lens=[12, 7])
     torch.cuda.synchronize()
     assert torch.equal(y_static, eager1)
+
+
+@pytest.mark.parametrize("env", [{"BVG_ACT_MMA": "0"}, {"BVG_ACT_MMA_UPLO": "1"}, {"BVG_FUSE_ACT": "1"},
+                                 {"BVG_RES_MMA_MAXC": "0"}])
+def test_optional_kernel_paths(env):
+    """The opt-in / fallback kernels (register-streamed bf16 activation, hi+lo up-FIR taps, activation fused into
+    the conv producer, residual in the epilogue) stay within the bf16 SNR bound on config 1."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "tests", "optional_path_check.py")],
+                         env=dict(os.environ, **env), capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    snr = float([ln for ln in out.stdout.splitlines() if ln.startswith("SNR_DB")][-1].split()[1])
+    print(env, "cfg1 bf16 SNR dB", snr)
+    assert snr >= BF16_SNR_DB
