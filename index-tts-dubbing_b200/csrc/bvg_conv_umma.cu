@@ -48,6 +48,8 @@
 #include <cstdlib>
 #include <type_traits>
 
+#include <cuda_fp16.h>
+
 #include "bvg_act_core.cuh"
 #include "bvg_common.cuh"
 #include "bvg_misc.cuh"
@@ -222,6 +224,38 @@ __device__ __forceinline__ void issue_tap(uint32_t d0, uint32_t bnc, uint64_t ad
   }
 }
 
+// ---- warp-level MMA pieces of the fused activation (same scheme as csrc/bvg_act3.cu) ----
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void stsm_x2_trans(uint32_t addr, uint32_t r0, uint32_t r1) {
+  asm volatile("stmatrix.sync.aligned.m8n8.x2.trans.shared.b16 [%0], {%1,%2};" ::"r"(addr), "r"(r0), "r"(r1) : "memory");
+}
+__device__ __forceinline__ void wmma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void wmma_f16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pk_f16(float lo, float hi) {
+  __half2 h = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ uint32_t pk_bf16(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float fir_tap(int k) {   // f[k], 0 outside 0..11
+  const float f[6] = {BVG_F0, BVG_F1, BVG_F2, BVG_F3, BVG_F4, BVG_F5};
+  if (k < 0 || k > 11) return 0.f;
+  return f[k < 6 ? k : 11 - k];
+}
+
 struct UmmaKernelArgs {
   ConvArgs c;
   const int* tile_prefix;   // [B+1] prefix sum of m-tiles per segment (tile = 128*MSUB rows)
@@ -242,7 +276,8 @@ struct UmmaKernelArgs {
   const float* act_inv_beta;
   int NR;                   // raw stages
   int rstride, r_stage_bytes;
-  int nblk;                 // ACT_RT-row blocks per chunk
+  int nblk;                 // 8-row output column tiles per chunk (astride = 8 * nblk)
+  int act_ngc, act_jr;      // fused activation work items: act_ngc row ranges per chunk of act_jr column tiles each
   // residual folded into the accumulator: after the conv k-blocks, NKB more k-blocks take the residual
   // tile as A operand against identity weight images (appended to the layer's image), so the epilogue
   // issues no global loads (narrow stages were bound by that latency chain)
@@ -372,21 +407,22 @@ __global__ void __launch_bounds__(FUSE ? NTHREADS_FUSED : 64 + 32 * EPW, 1) conv
         for (int kb = 0; kb < ka.NKB; ++kb) {
           const int kcl = (kb == ka.NKB - 1) ? ka.kc_last_load : ka.KC;
           if constexpr (FUSE) {
-            // raw rows [row0 - 5, row0 + nblk*ACT_RT + 5) of every chunk: the activation warps consume them
-            const int rrows = ka.nblk * ACT_RT + 10;
+            // raw rows [row0 - 8, row0 + 8*nblk + 24) of every chunk: the activation warps consume them
+            const int rrows = ka.rstride;
             mbar_wait(R_EMPTY(sr), pr ^ 1);
             TRACE(0, 2, t);
             mbar_expect_tx(R_FULL(sr), (uint32_t)(kcl * rrows * 16));
             const uint32_t rdst = smem_u32(r_smem + (size_t)sr * ka.r_stage_bytes);
-            // Slab row j holds segment time tR0 + j.  The five rows on either side of the segment carry
-            // the replicate padding of Activation1d's input (x[0] / x[L-1]) instead of the layout's zero
-            // guard rows, so the activation warps can stream every block with the interior formulas; the
-            // pieces are disjoint (no ordering exists between bulk copies).  Interior tiles: one piece.
-            const int tR0 = q0c + ka.minoff - 5;
+            // Slab row j holds segment time tR0 + j.  Every row before the segment and the five rows after it
+            // carry the replicate padding of Activation1d's input (x[0] / x[L-1]) instead of the layout's zero
+            // guard rows, so the activation warps can run every column tile with the interior formulas (and
+            // never multiply an out-of-segment bit pattern by a zero tap); the pieces are disjoint (no
+            // ordering exists between bulk copies).  Interior tiles: one piece.
+            const int tR0 = q0c + ka.minoff - 8;
             auto clampj = [&](int v) { return v < 0 ? 0 : (v > rrows ? rrows : v); };
-            const int jl0 = clampj(-5 - tR0), jl1 = clampj(-tR0), jr0 = clampj(Lc - tR0), jr1 = clampj(Lc + 5 - tR0);
+            const int jl0 = 0, jl1 = clampj(-tR0), jr0 = clampj(Lc - tR0), jr1 = clampj(Lc + 5 - tR0);
             for (int c = 0; c < kcl; ++c) {
-              const __nv_bfloat16* src = xg + ((size_t)(kb * ka.KC + c) * a.Rx + row0c - 5) * 8;   // slab row 0
+              const __nv_bfloat16* src = xg + ((size_t)(kb * ka.KC + c) * a.Rx + row0c - 8) * 8;   // slab row 0
               const uint32_t dst = rdst + (uint32_t)(c * ka.rstride) * 16;
               if (jl0 > 0) bulk_g2s(dst, src, (uint32_t)(jl0 * 16), R_FULL(sr));
               for (int j = jl0; j < jl1; ++j) bulk_g2s(dst + j * 16, src + (size_t)(-tR0) * 8, 16u, R_FULL(sr));          // x[0]
@@ -724,12 +760,25 @@ __global__ void __launch_bounds__(FUSE ? NTHREADS_FUSED : 64 + 32 * EPW, 1) conv
   }
   else if constexpr (FUSE) {
     // ===================== activation warps (fused mode) =====================
-    // Raw tile (R stage) -> Activation1d -> activated tile (A stage, UMMA layout).  A work unit is one
-    // 8-channel chunk x ACT_RT consecutive rows; lane = (unit slot tb = lane>>2, channel pair cp).
-    // ACT_RT is odd, so the 8 slots of a warp hit distinct banks with their 4-byte column accesses.
+    // Raw tile (R stage) -> Activation1d -> activated tile (A stage, UMMA layout), with both FIR filters as
+    // warp-level MMAs (the scheme of csrc/bvg_act3.cu): the 16 MMA rows are two work items of 8 channels
+    // (a chunk x a range of act_jr 8-row column tiles), the MMA columns are time; ldmatrix.trans reads the
+    // raw rows, stmatrix.trans writes activated bf16 rows straight into the A operand slab.
     const int aw = warp - 2 - epiw;
-    const int cp = lane & 3, tb = lane >> 2;
-    const int rrows = ka.nblk * ACT_RT + 10;
+    const int g = lane >> 2, t4 = lane & 3;
+    const int rrows = ka.rstride;
+    // constant tap fragments: up-FIR B[k][n] = 2 f[n + 11 - 2k] (bf16), down-FIR B_d[k][n] = f[16 d + k - 2n + 5] (fp16)
+    uint32_t gup[2], fdn[3][2];
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int k0 = 2 * t4 + 8 * half;
+      gup[half] = pk_bf16(2.f * fir_tap(g + 11 - 2 * k0), 2.f * fir_tap(g + 11 - 2 * (k0 + 1)));
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        const int off = 16 * (d - 1) + 5 - 2 * g;
+        fdn[d][half] = pk_f16(fir_tap(k0 + off), fir_tap(k0 + 1 + off));
+      }
+    }
     int sr = 0, pr = 0, sa = 0, pa = 0;
     int t = blockIdx.x;
     TileRef cur = t < total_tiles ? decode(t) : TileRef{0, 0, 0};
@@ -739,7 +788,7 @@ __global__ void __launch_bounds__(FUSE ? NTHREADS_FUSED : 64 + 32 * EPW, 1) conv
       const int L = Lseg;
       const int tn = t + gridDim.x;
       if (tn < total_tiles) { cur = decode(tn); Lseg = a.seg_in[cur.b].len; }
-      const int tA0 = tl.q0 + ka.minoff;      // segment time of A-slab row 0
+      const int tA0 = tl.q0 + ka.minoff;      // segment time of A-slab row 0 (raw slab row r = time tA0 - 8 + r)
       const bool tr = aw == 0 && lane == 0;
       for (int kb = 0; kb < ka.NKB; ++kb) {
         const int kcl = (kb == ka.NKB - 1) ? ka.kc_last_load : ka.KC;
@@ -750,32 +799,76 @@ __global__ void __launch_bounds__(FUSE ? NTHREADS_FUSED : 64 + 32 * EPW, 1) conv
         if (tr) TRACE(3, 2, t);
         const __nv_bfloat16* rbase = reinterpret_cast<const __nv_bfloat16*>(r_smem + (size_t)sr * ka.r_stage_bytes);
         __nv_bfloat16* abase = reinterpret_cast<__nv_bfloat16*>(a_smem + (size_t)sa * ka.a_stage_bytes);
-        const int nunits = kcl * ka.nblk;
-        for (int unit = aw * 8 + tb; unit < nunits; unit += 8 * NACT) {
-          const int c = unit / ka.nblk, blk = unit - c * ka.nblk;
-          const __nv_bfloat16* rcol = rbase + (size_t)(c * ka.rstride) * 8 + 2 * cp;   // slab row 0 of this chunk
-          __nv_bfloat16* ycol = abase + (size_t)(c * ka.astride + blk * ACT_RT) * 8 + 2 * cp;
-          const int ch = (kb * ka.KC + c) * 8 + 2 * cp;
-          const float a0 = 2.f * ka.act_alpha[ch], a1 = 2.f * ka.act_alpha[ch + 1];
-          const float h0 = 0.5f * ka.act_inv_beta[ch], h1 = 0.5f * ka.act_inv_beta[ch + 1];
-          const int r0 = tA0 + blk * ACT_RT;   // segment time of this block's first output
-          if (r0 + ACT_RT <= 0 || r0 >= L) {
-            // block entirely outside the segment: the conv's "same" zero padding of the ACTIVATED signal
+        const uint32_t r_s = smem_u32(rbase), a_s = smem_u32(abase);
+        const int nitems = kcl * ka.act_ngc;
+        for (int unit = aw; 2 * unit < nitems; unit += NACT) {
+          // the two work items of this warp (the second one repeats the first when the count is odd)
+          int ic[2], iJ0[2];
+#pragma unroll
+          for (int s2 = 0; s2 < 2; ++s2) {
+            const int it = 2 * unit + s2 < nitems ? 2 * unit + s2 : 2 * unit;
+            ic[s2] = it / ka.act_ngc;
+            iJ0[s2] = (it - ic[s2] * ka.act_ngc) * ka.act_jr;
+          }
+          float a2[2], hh[2];
+#pragma unroll
+          for (int s2 = 0; s2 < 2; ++s2) {
+            const int ch = (kb * ka.KC + ic[s2]) * 8 + g;
+            a2[s2] = 2.f * ka.act_alpha[ch];
+            hh[s2] = 0.5f * ka.act_inv_beta[ch];
+          }
+          // ldmatrix row address of this lane: matrices 0..3 = (item 0, rows +0..7), (item 1, +0..7), (item 0, +8..15), (item 1, +8..15)
+          const int sl = (lane >> 3) & 1;
+          const uint32_t ld_base = r_s + (uint32_t)(ic[sl] * ka.rstride + 8 * iJ0[sl] + (lane >> 4) * 8 + (lane & 7)) * 16;
+          // stmatrix row address: matrices 0 / 1 = item 0 / 1
+          const uint32_t st_base = a_s + (uint32_t)(ic[sl] * ka.astride + 8 * iJ0[sl] + (lane & 7)) * 16;
+          // one up-FIR column tile j (relative to the item's first column tile): 8 activated samples of both items
+          auto up_tile = [&](int j, uint32_t& p0, uint32_t& p1) {
+            uint32_t xa[4];
+            ldsm_x4_trans(ld_base + (uint32_t)(4 * j + 5) * 16, xa);   // raw rows of local time 4j-3 .. 4j+12 (+8 margin)
+            float c[4] = {0.f, 0.f, 0.f, 0.f};
+            wmma_bf16(c, xa, gup[0], gup[1]);
+            const float s0 = fmaf(-hh[0], __cosf(a2[0] * c[0]), c[0]), s1 = fmaf(-hh[0], __cosf(a2[0] * c[1]), c[1]);
+            const float s2 = fmaf(-hh[1], __cosf(a2[1] * c[2]), c[2]), s3 = fmaf(-hh[1], __cosf(a2[1] * c[3]), c[3]);
+            p0 = pk_f16(s0, s1);
+            p1 = pk_f16(s2, s3);
+          };
+          uint32_t ap[4], ac[4], an[4];
+          ap[0] = ap[1] = 0u;   // (zero taps)
+          up_tile(-1, ap[2], ap[3]);
+          up_tile(0, ac[0], ac[1]);
+          up_tile(1, ac[2], ac[3]);
 #pragma unroll 1
-            for (int tt = 0; tt < ACT_RT; ++tt) *reinterpret_cast<uint32_t*>(ycol + tt * 8) = 0u;
-          } else {
-            // the raw slab already carries the replicate padding of the input (producer), so the interior
-            // formulas hold everywhere except the three outputs next to each segment end, which see the
-            // replicate padding of the activated 2x signal: those are patched with the exact form
-            actcore::stream_packed<ACT_RT>(rcol + (size_t)(blk * ACT_RT) * 8, ycol, a0, a1, h0, h1);
-            if (r0 < 3 || r0 + ACT_RT > L - 3) {
+          for (int J = 0; J < ka.act_jr; ++J) {
+            up_tile(2 * J + 2, an[0], an[1]);
+            up_tile(2 * J + 3, an[2], an[3]);
+            float c[4] = {hh[0], hh[0], hh[1], hh[1]};
+            wmma_f16(c, ap, fdn[0][0], fdn[0][1]);
+            wmma_f16(c, ac, fdn[1][0], fdn[1][1]);
+            wmma_f16(c, an, fdn[2][0], fdn[2][1]);
+            stsm_x2_trans(st_base + (uint32_t)(8 * J) * 16, pk_bf16(c[0], c[1]), pk_bf16(c[2], c[3]));
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { ap[i] = ac[i]; ac[i] = an[i]; }
+          }
+          // rows outside the segment are the conv's "same" zero padding of the ACTIVATED signal; the three rows next to
+          // each segment end see the replicate padding of the activated 2x signal: exact form.  lane = (row, channel pair)
+          __syncwarp();
+#pragma unroll
+          for (int s2 = 0; s2 < 2; ++s2) {
+            if (s2 == 1 && 2 * unit + 1 >= nitems) break;
+            const int t_first = tA0 + 8 * iJ0[s2], t_end = t_first + 8 * ka.act_jr;
+            if (t_first >= 3 && t_end <= L - 3) continue;
+            const int ch = (kb * ka.KC + ic[s2]) * 8 + 2 * t4;
+            const float fa0 = 2.f * ka.act_alpha[ch], fa1 = 2.f * ka.act_alpha[ch + 1];
+            const float fh0 = 0.5f * ka.act_inv_beta[ch], fh1 = 0.5f * ka.act_inv_beta[ch + 1];
+            const __nv_bfloat16* rcol = rbase + (size_t)(ic[s2] * ka.rstride) * 8 + 2 * t4;
+            __nv_bfloat16* ycol = abase + (size_t)(ic[s2] * ka.astride + 8 * iJ0[s2]) * 8 + 2 * t4;
 #pragma unroll 1
-              for (int tt = 0; tt < ACT_RT; ++tt) {
-                const int ts = r0 + tt;
-                if (ts < 0 || ts >= L) *reinterpret_cast<uint32_t*>(ycol + tt * 8) = 0u;
-                else if (ts < 3 || ts >= L - 3)
-                  actcore::stpair(ycol + tt * 8, actcore::exact_clamped(rcol, tA0 - 5, rrows, ts, L, a0, a1, h0, h1));
-              }
+            for (int J = 0; J < ka.act_jr; ++J) {
+              const int row = 8 * J + g, ts = t_first + row;
+              if (ts < 0 || ts >= L) *reinterpret_cast<uint32_t*>(ycol + row * 8) = 0u;
+              else if (ts < 3 || ts >= L - 3)
+                actcore::stpair(ycol + row * 8, actcore::exact_clamped(rcol, tA0 - 8, rrows, ts, L, fa0, fa1, fh0, fh1));
             }
           }
         }
@@ -919,7 +1012,7 @@ bool configure_fused(const ConvArgs& a, int msub, UmmaKernelArgs& ka, size_t& sm
   if (!t.ok || t.NT != 1) return false;
   int mn, mx;
   tap_range(a, mn, mx);
-  if (mx - mn > MAXSPAN || -mn + 5 > BVG_GUARD || mx > BVG_GUARD) return false;
+  if (mx - mn > MAXSPAN || -mn > BVG_GUARD || mx > BVG_GUARD) return false;
   ka.c = a;
   ka.KC = t.KC; ka.NKB = t.NKB; ka.BN = t.BN; ka.BNC = t.BNC; ka.NT = t.NT;
   ka.minoff = mn; ka.span = mx - mn;
@@ -930,10 +1023,16 @@ bool configure_fused(const ConvArgs& a, int msub, UmmaKernelArgs& ka, size_t& sm
   ka.tmem_cols = 32;
   while (ka.tmem_cols < ka.ACC * ka.MSUB * ka.BNC) ka.tmem_cols <<= 1;
   const int arows = 128 * msub + ka.span;
-  ka.nblk = (arows + ACT_RT - 1) / ACT_RT;
-  ka.astride = ka.nblk * ACT_RT;
-  ka.rstride = ka.nblk * ACT_RT + 10;
-  if (ka.nblk * ACT_RT + 8 > BVG_TAIL_SLACK + BVG_GUARD) return false;   // raw loads past a segment end stay in bounds
+  // activation work items: act_ngc row ranges per chunk, two items per warp pass, about one pass per tile
+  const int kc_items = t.KC;
+  ka.act_ngc = 2 * NACT / kc_items;
+  if (ka.act_ngc < 1) ka.act_ngc = 1;
+  const int njt = (arows + 7) / 8;
+  ka.act_jr = (njt + ka.act_ngc - 1) / ka.act_ngc;
+  ka.nblk = ka.act_ngc * ka.act_jr;
+  ka.astride = 8 * ka.nblk;
+  ka.rstride = ka.astride + 32;          // local time -8 .. astride + 23
+  if (ka.rstride + 8 > BVG_TAIL_SLACK + BVG_GUARD) return false;   // raw loads past a segment end stay in bounds
   ka.a_stage_bytes = t.KC * ka.astride * 16;
   ka.r_stage_bytes = t.KC * ka.rstride * 16;
   ka.b_stage_bytes = t.KC * t.BN * 16;
