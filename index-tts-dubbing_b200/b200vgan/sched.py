@@ -74,11 +74,10 @@ def decode_segments(model, latents: Sequence[torch.Tensor], emb: torch.Tensor, i
                         dtype=latents[batch[0]].dtype)
         for k, i in enumerate(batch):
             x[k, : frames[i]] = latents[i]
-        wav = model.forward_with_embedding(x, emb, x_lens=[frames[i] for i in batch])
-        if int16:  # the caller's clamp(32767*wav) of infer.py:627-628
-            wav = torch.clamp(32767.0 * wav, -32767.0, 32767.0).to(torch.int16)
+        # int16: the callers' clamp(32767*wav) + int16 cast (infer.py:627-628, :650), fused into the decode's last kernel
+        wav = model.forward_with_embedding(x, emb, x_lens=[frames[i] for i in batch], pcm16=int16)
         for k, i in enumerate(batch):
-            w = wav[k, 0, : frames[i] * model.hop]
+            w = (wav[k] if int16 else wav[k, 0])[: frames[i] * model.hop]
             out[i] = w.to("cpu", non_blocking=False) if to_host else w
     return out
 

@@ -170,6 +170,12 @@ def test_cfg3_srt_workload_batched_equals_single(gen):
     for i in (mine[0], mine[len(mine) // 2], mine[-1]):
         single = gen.forward_with_embedding(lat[i][None], emb)[0, 0].cpu()
         assert torch.equal(out[i], single)
+    # the same job with 16-bit PCM straight from the last kernel (what the dubbing tool writes to disk)
+    few = mine[:6]
+    pcm = sched.decode_segments(gen, lat, emb, indices=few, max_batch_frames=4096, max_batch=32, int16=True)
+    for i in few:
+        ref = torch.clamp(32767 * out[i], -32767.0, 32767.0).type(torch.int16)
+        assert pcm[i].dtype == torch.int16 and torch.equal(pcm[i], ref)
 
 
 def test_checkpoint_layout_gives_same_audio(gen, synth_sd):
