@@ -223,14 +223,24 @@ act1d_c8_mma_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restri
     // the raw rows these outputs overwrite were consumed by the column tiles above
     stsm_x2_trans(st_base + (uint32_t)(8 * J) * 16, pack_bf16(c[0], c[1]), pack_bf16(c[2], c[3]));
   };
-  static_assert(NJ % 3 == 1, "the J loop is unrolled by 3 with rotating fragment names");
+  // the J loop is unrolled by 3 with rotating fragment names; the last one to three column tiles follow separately
+  constexpr int NJ3 = ((NJ - 1) / 3) * 3;
 #pragma unroll 1
-  for (int J = 0; J < NJ - 1; J += 3) {
+  for (int J = 0; J < NJ3; J += 3) {
     step(J, ap, ac, an, false);
     step(J + 1, ac, an, ap, false);
     step(J + 2, an, ap, ac, false);
   }
-  step(NJ - 1, ap, ac, an, true);
+  if constexpr (NJ - NJ3 == 1) {
+    step(NJ - 1, ap, ac, an, true);
+  } else if constexpr (NJ - NJ3 == 2) {
+    step(NJ - 2, ap, ac, an, false);
+    step(NJ - 1, ac, an, ap, true);
+  } else {
+    step(NJ - 3, ap, ac, an, false);
+    step(NJ - 2, ac, an, ap, false);
+    step(NJ - 1, an, ap, ac, true);
+  }
   __syncwarp();
   // ---- patch the exact edge values in ----
   if (lane < 16) {
