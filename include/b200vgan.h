@@ -14,7 +14,8 @@
  *   - every function returns 0 on success, non-zero on failure; the message is available from
  *     bvg_last_error() (thread-local).  Nothing throws across the ABI.
  *   - the caller owns all tensors and the workspace; the library owns only its repacked
- *     weights (inside bvg_handle) and the per-geometry segment tables (inside bvg_plan).
+ *     weights and the arena of per-geometry segment tables (inside bvg_handle; a bvg_plan holds
+ *     a slice of it, so destroy plans before their handle).
  *   - all work is asynchronous on the given stream; bvg_forward performs no allocation and no
  *     host synchronisation, so it is CUDA-graph capturable.
  *   - a handle is bound to the device current at bvg_create(); it is not thread-safe.
@@ -110,9 +111,9 @@ int32_t bvg_plan_num_launches(const bvg_plan* p);
  *   latent   [B, max_frames, gpt_dim]      latent_dtype (BVG_F32 | BVG_BF16 | BVG_F16), row-major
  *   spk_emb  [spk_batch, 1, spk_dim] fp32  ECAPA embedding, spk_batch in {1, B}
  *   wav      [B, 1, max_frames*hop] fp32   tanh output; samples beyond a segment's length are 0
- *   workspace: >= bvg_plan_workspace_bytes(plan) bytes of device memory, 256-byte aligned.  The
- *   first call with a given (workspace, plan) pair clears the guard rows; later calls reuse them
- *   (see bvg_workspace_reset). */
+ *   workspace: >= bvg_plan_workspace_bytes(plan) bytes of device memory, 256-byte aligned; its contents on
+ *   entry do not matter (every call re-clears the zero guard rows of the packed layout with one small launch),
+ *   so one workspace can serve any sequence of plans and may be a recycled allocation. */
 int bvg_forward(bvg_handle* h, bvg_plan* plan, const void* latent, int32_t latent_dtype,
                 const float* spk_emb, int32_t spk_batch, float* wav, void* workspace,
                 size_t workspace_bytes, void* stream);
@@ -133,10 +134,22 @@ int bvg_forward_pcm16(bvg_handle* h, bvg_plan* plan, const void* latent, int32_t
 int bvg_profile_enable(bvg_handle* h, int32_t on);
 int bvg_profile_read(bvg_handle* h, double* ms, double* flops, double* bytes, int64_t* launches);
 
-/* The library remembers, per workspace address, which plan last laid out its zero guard rows and
- * re-clears them only when the plan changes.  Call this after freeing / reallocating a workspace
- * (its old address may be reused with stale contents). */
-int bvg_workspace_reset(bvg_handle* h);
+/* Ragged (variable-length) batch I/O for multi-utterance / SRT-dubbing jobs -- replaces the per-entry loop of
+ * srt_dubbing/src/strategies/stretch_strategy.py:72-83 and the time-concatenation of indextts/infer.py:439-463:
+ *   latent_rows [sum_b frames[b], gpt_dim]   the segments' latent frames back to back in plan order (no padding)
+ *   wav_rows    [sum_b frames[b]*hop] fp32   and / or
+ *   pcm_rows    [sum_b frames[b]*hop] int16  (clamp(32767*wav) as in bvg_forward_pcm16); either may be NULL, not both.
+ * Segment b's samples start at hop * (frames[0] + ... + frames[b-1]); nothing else is written.  Each segment is decoded
+ * exactly as if it were alone in the batch. */
+int bvg_forward_ragged(bvg_handle* h, bvg_plan* plan, const void* latent_rows, int32_t latent_dtype,
+                       const float* spk_emb, int32_t spk_batch, float* wav_rows_or_null, int16_t* pcm_rows_or_null,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* Plan bookkeeping: plans created on this handle so far (their tables come from a recycled device + pinned-host arena,
+ * so creating one costs no device allocation and no synchronous copy once the arena is warm), and the number of
+ * latent frames (sum over segments) a plan decodes. */
+int64_t bvg_plans_created(const bvg_handle* h);
+int64_t bvg_plan_total_frames(const bvg_plan* plan);
 
 /* Host-buffer variant used for end-to-end timing: copies latent (host, ideally pinned) to the
  * device, runs bvg_forward, copies wav back into `wav_host` and synchronises the stream.

@@ -19,7 +19,7 @@ SYMBOLS = [
     "bvg_last_error", "bvg_version", "bvg_device_check", "bvg_create", "bvg_destroy", "bvg_set_weight",
     "bvg_finalize", "bvg_plan_create", "bvg_plan_destroy", "bvg_plan_workspace_bytes", "bvg_plan_max_frames",
     "bvg_plan_num_launches", "bvg_forward", "bvg_forward_host", "bvg_activation1d", "bvg_conv1d",
-    "bvg_conv_transpose1d", "bvg_workspace_reset", "bvg_profile_enable", "bvg_profile_read",
+    "bvg_conv_transpose1d", "bvg_forward_ragged", "bvg_plans_created", "bvg_plan_total_frames", "bvg_profile_enable", "bvg_profile_read",
     "bvg_activation1d_packed", "bvg_act_conv1d", "bvg_ecapa_workspace_bytes", "bvg_speaker_embedding",
     "bvg_forward_pcm16",
 ]
@@ -74,7 +74,11 @@ def load(rebuild: bool = False) -> C.CDLL:
     lib.bvg_plan_workspace_bytes.restype = sz
     lib.bvg_plan_max_frames.argtypes = [vp]
     lib.bvg_plan_num_launches.argtypes = [vp]
-    lib.bvg_workspace_reset.argtypes = [vp]
+    lib.bvg_forward_ragged.argtypes = [vp, vp, vp, i32, vp, i32, vp, vp, vp, sz, vp]
+    lib.bvg_plans_created.argtypes = [vp]
+    lib.bvg_plans_created.restype = C.c_int64
+    lib.bvg_plan_total_frames.argtypes = [vp]
+    lib.bvg_plan_total_frames.restype = C.c_int64
     lib.bvg_profile_enable.argtypes = [vp, i32]
     lib.bvg_profile_read.argtypes = [vp, vp, vp, vp, vp]
     lib.bvg_forward.argtypes = [vp, vp, vp, i32, vp, i32, vp, vp, sz, vp]

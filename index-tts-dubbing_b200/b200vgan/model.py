@@ -163,6 +163,7 @@ class BigVGAN(nn.Module):
             self.conds = nn.ModuleList([nn.Conv1d(spk, c0 >> (i + 1), 1) for i in range(cfg.num_upsamples)])
         # engine state
         self._handle = None
+        self._engine_device = None
         self._engine_dirty = True
         self._plans: Dict[Tuple[Tuple[int, ...], int], C.c_void_p] = {}
         self._workspace: Optional[torch.Tensor] = None
@@ -243,8 +244,7 @@ class BigVGAN(nn.Module):
             raise _lib.BvgError("speaker embedding batch must be 1 or B")
         with torch.cuda.device(x.device):
             self._ensure_engine(x.device)
-            mode = _lib.MODE_FP32 if self.precision == "fp32" else _lib.MODE_BF16
-            plan = self._plan(frames, mode)
+            plan = self._plan(frames, self._mode())
             ws = self._ensure_workspace(int(self._libh.bvg_plan_workspace_bytes(plan)), x.device)
             stream = torch.cuda.current_stream(x.device).cuda_stream
             if pcm16:
@@ -257,9 +257,57 @@ class BigVGAN(nn.Module):
                                               emb.shape[0], wav.data_ptr(), ws.data_ptr(), ws.numel(), stream))
         return wav
 
+    @torch.no_grad()
+    def forward_ragged(self, rows, frames: Sequence[int], emb, pcm16: bool = False, out: Optional[torch.Tensor] = None):
+        """Variable-length batch without padding (bvg_forward_ragged): `rows` [sum(frames), gpt_dim] holds the
+        segments' latent frames back to back, the result is ONE vector [sum(frames)*hop] (fp32 waveform, or int16
+        PCM with `pcm16`) with segment b's samples starting at hop*sum(frames[:b]).  `out` may be a preallocated
+        slice of a larger result arena.  Replaces the per-entry loop of srt_dubbing stretch_strategy.py:72-83 and the
+        chunk concatenation of infer.py:439-463; each segment is decoded exactly as if alone."""
+        if not rows.is_cuda:
+            raise _lib.BvgError("b200vgan has no CPU path: latents must live on a CUDA (sm_100) device")
+        if rows.dtype not in _DT:
+            rows = rows.float()
+        rows = rows.contiguous()
+        frames = tuple(int(v) for v in frames)
+        if rows.dim() != 2 or rows.shape[1] != self._cfg.gpt_dim or rows.shape[0] != sum(frames):
+            raise _lib.BvgError("forward_ragged: rows must be [sum(frames), gpt_dim]")
+        emb = emb.to(device=rows.device, dtype=torch.float32).contiguous()
+        if emb.shape[0] not in (1, len(frames)):
+            raise _lib.BvgError("speaker embedding batch must be 1 or the number of segments")
+        n = rows.shape[0] * self.hop
+        dt = torch.int16 if pcm16 else torch.float32
+        if out is None:
+            out = torch.empty(n, device=rows.device, dtype=dt)
+        elif out.dtype != dt or out.numel() != n or not out.is_contiguous() or out.device != rows.device:
+            raise _lib.BvgError("forward_ragged: `out` must be a contiguous device vector of sum(frames)*hop elements")
+        with torch.cuda.device(rows.device):
+            self._ensure_engine(rows.device)
+            plan = self._plan(frames, self._mode())
+            ws = self._ensure_workspace(int(self._libh.bvg_plan_workspace_bytes(plan)), rows.device)
+            stream = torch.cuda.current_stream(rows.device).cuda_stream
+            _lib.check(self._libh.bvg_forward_ragged(self._handle, plan, rows.data_ptr(), _DT[rows.dtype], emb.data_ptr(),
+                                                     emb.shape[0], None if pcm16 else out.data_ptr(),
+                                                     out.data_ptr() if pcm16 else None, ws.data_ptr(), ws.numel(), stream))
+        return out
+
+    def activation_kernel_name(self) -> str:
+        """Which Activation1d kernel bvg_forward launches in the current precision mode (for bench reports)."""
+        import os
+        if self.precision == "fp32":
+            return "act1d_c8_v3_kernel (Activation1d, register-streamed fp32)"
+        if os.environ.get("BVG_ACT_MMA", "1") == "0":
+            return "act1d_c8_v3_kernel (Activation1d, register-streamed, packed f32x2)"
+        return "act1d_c8_mma_kernel (Activation1d: up-FIR and down-FIR as warp-level MMAs, SnakeBeta on CUDA cores)"
+
+    def plans_created(self) -> int:
+        return 0 if self._handle is None else int(self._libh.bvg_plans_created(self._handle))
+
+    def _mode(self) -> int:
+        return _lib.MODE_FP32 if self.precision == "fp32" else _lib.MODE_BF16
+
     def num_launches(self, frames: Sequence[int]) -> int:
-        mode = _lib.MODE_FP32 if self.precision == "fp32" else _lib.MODE_BF16
-        return int(self._libh.bvg_plan_num_launches(self._plan(tuple(int(f) for f in frames), mode)))
+        return int(self._libh.bvg_plan_num_launches(self._plan(tuple(int(f) for f in frames), self._mode())))
 
     PROFILE_CLASSES = ("activation1d", "conv_tcgen05", "conv_cuda_core", "other")
 
@@ -299,9 +347,30 @@ class BigVGAN(nn.Module):
                 out["speaker_encoder." + k] = v.detach()
         return out
 
+    def _release_engine(self):
+        """Destroy the native handle, its plans and the workspace (they are bound to ONE device)."""
+        for p in self._plans.values():
+            self._libh.bvg_plan_destroy(p)
+        self._plans.clear()
+        if self._handle is not None:
+            self._libh.bvg_destroy(self._handle)
+        self._handle = None
+        self._workspace = None
+        self._engine_device = None
+        self._spk_cache.clear()
+
     def _ensure_engine(self, device):
+        device = torch.device(device)
+        if device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        if self._handle is not None and self._engine_device != device:
+            # .to(another GPU): repacked weights, plan tables and the workspace live on the old device
+            with torch.cuda.device(self._engine_device):
+                torch.cuda.synchronize()
+                self._release_engine()
         if self._handle is not None and not self._engine_dirty:
             return
+        self._engine_device = device
         if self._handle is None:
             hd = C.c_void_p()
             _lib.check(self._libh.bvg_create(C.byref(self._cfg), C.byref(hd)))
@@ -335,16 +404,11 @@ class BigVGAN(nn.Module):
         if ws is None or ws.numel() < nbytes or ws.device != device:
             self._workspace = None
             ws = torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=device)
-            self._workspace = ws
-            if self._handle is not None:   # the old address may come back with stale guard rows
-                _lib.check(self._libh.bvg_workspace_reset(self._handle))
+            self._workspace = ws     # contents do not matter: every forward re-clears the layout's guard rows
         return ws
 
     def __del__(self):
         try:
-            for p in self._plans.values():
-                self._libh.bvg_plan_destroy(p)
-            if self._handle is not None:
-                self._libh.bvg_destroy(self._handle)
+            self._release_engine()
         except Exception:
             pass

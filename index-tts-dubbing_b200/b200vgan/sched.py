@@ -1,16 +1,28 @@
-"""Segment scheduling for multi-utterance / SRT-dubbing decode (SURVEY.md section 8e).
+"""Segment scheduling for multi-utterance / SRT-dubbing decode (SURVEY.md section 8e, 8f row 2).
 
 Utterances are independent, so the path shards with NO data-path collective: one process per GPU,
-each decodes its own shard in length-bucketed, exact-variable-length batches and returns the
-waveforms to the host.  The only communication is the final host-side gather of results
-(`gather_waveforms`, torch.distributed: NCCL on GPUs, gloo in the CPU tests).
+each decodes its own shard in length-bucketed, exact-variable-length ("ragged") batches.  The only
+communication is the final gather of the 16-bit results onto rank 0 (`gather_results`,
+torch.distributed: NCCL on GPUs, gloo in the CPU tests) -- never on the hot path.
 
-The reference decodes one subtitle entry at a time on one device
-(srt_dubbing/src/strategies/stretch_strategy.py:72-83, indextts/infer.py:622-631); this module
-defines the batched, sharded replacement of that loop.
+What this replaces in the reference:
+  * srt_dubbing/src/strategies/stretch_strategy.py:72-83 -- one `tts.infer` (one B=1 vocoder call) per
+    subtitle entry, each followed by its own blocking `.cpu()`;
+  * indextts/infer.py:439-463 (`infer_fast`) -- `chunk_size = 2` sentence latents concatenated along TIME and
+    decoded as one B=1 sequence (which smears the sentences' boundaries into each other), then
+    `clamp(32767 * wav)` + `.cpu()` per chunk (infer.py:462-463).
+Here every segment is decoded exactly as if alone (per-segment lengths reach the kernels, the packed
+layout separates segments by zero guard rows), B > 1 per launch sequence, int16 PCM comes straight out of
+the last kernel, and one asynchronous device-to-host copy per batch lands in a pinned result arena.
+
+Data movement per batch (`decode_shard`): the segments' latents are gathered into one contiguous
+[sum T_i, gpt_dim] device matrix (one `torch.cat` of device tensors, or one cudaMemcpyAsync per pinned
+host tensor -- no zero fill, no padding), `BigVGAN.forward_ragged` writes the batch's slice of the
+shard's result vector, and a copy stream moves that slice to the host while the next batch decodes.
 """
 from __future__ import annotations
 
+from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -58,47 +70,163 @@ def srt_workload(n: int = 512, seed: int = 2026, lo: float = 1.0, hi: float = 15
     return [int(np.ceil(d * sr / hop)) for d in dur]
 
 
+@dataclass
+class ShardResult:
+    """One rank's decoded segments: ONE flat vector (int16 PCM or fp32) plus an index.
+    `flat` lives on the device (`host` is its pinned mirror when `to_host` was requested and is complete after
+    `wait()`); `index[i] = (offset, samples)` for every segment this rank decoded."""
+    flat: torch.Tensor
+    host: Optional[torch.Tensor]
+    index: Dict[int, Tuple[int, int]]
+    done: Optional[torch.cuda.Event] = None
+    batches: int = 0
+
+    def wait(self) -> "ShardResult":
+        if self.done is not None:
+            self.done.synchronize()
+            self.done = None
+        return self
+
+    def segment(self, i: int, on_host: bool = True) -> torch.Tensor:
+        off, n = self.index[i]
+        if on_host and self.host is not None:
+            self.wait()
+            return self.host[off:off + n]
+        return self.flat[off:off + n]
+
+
 @torch.no_grad()
-def decode_segments(model, latents: Sequence[torch.Tensor], emb: torch.Tensor, indices: Optional[Sequence[int]] = None,
-                    max_batch_frames: int = 4096, max_batch: int = 64, to_host: bool = True,
-                    int16: bool = False) -> Dict[int, torch.Tensor]:
-    """Decode the given segments (`latents[i]`: [T_i, gpt_dim] on the model's device) in batches.
-    Returns {segment index: waveform [T_i*hop]} (on the host, pinned, if `to_host`)."""
+def decode_shard(model, latents: Sequence[Optional[torch.Tensor]], emb: torch.Tensor,
+                 indices: Optional[Sequence[int]] = None, max_batch_frames: int = 4096, max_batch: int = 64,
+                 to_host: bool = True, int16: bool = True) -> ShardResult:
+    """Decode the segments `indices` of `latents` (latents[i]: [T_i, gpt_dim], on the model's device or in
+    (ideally pinned) host memory; entries this rank does not own may be None) in ragged batches.
+    Stream-ordered: returns without synchronising; `ShardResult.wait()` / `.segment()` do."""
     if indices is None:
-        indices = list(range(len(latents)))
-    frames = [int(l.shape[0]) for l in latents]
-    out: Dict[int, torch.Tensor] = {}
-    for batch in make_batches(indices, frames, max_batch_frames, max_batch):
-        T = max(frames[i] for i in batch)
-        x = torch.zeros(len(batch), T, latents[batch[0]].shape[1], device=latents[batch[0]].device,
-                        dtype=latents[batch[0]].dtype)
-        for k, i in enumerate(batch):
-            x[k, : frames[i]] = latents[i]
-        # int16: the callers' clamp(32767*wav) + int16 cast (infer.py:627-628, :650), fused into the decode's last kernel
-        wav = model.forward_with_embedding(x, emb, x_lens=[frames[i] for i in batch], pcm16=int16)
-        for k, i in enumerate(batch):
-            w = (wav[k] if int16 else wav[k, 0])[: frames[i] * model.hop]
-            out[i] = w.to("cpu", non_blocking=False) if to_host else w
-    return out
+        indices = [i for i, l in enumerate(latents) if l is not None]
+    indices = list(indices)
+    dev = model.conv_pre.bias.device
+    hop = model.hop
+    frames = {i: int(latents[i].shape[0]) for i in indices}
+    batches = make_batches(indices, frames, max_batch_frames, max_batch)
+    total = sum(frames.values())
+    dt = torch.int16 if int16 else torch.float32
+    flat = torch.empty(total * hop, device=dev, dtype=dt)
+    host = torch.empty(total * hop, dtype=dt, pin_memory=True) if to_host else None
+    index: Dict[int, Tuple[int, int]] = {}
+    main = torch.cuda.current_stream(dev)
+    copy_stream = torch.cuda.Stream(dev) if to_host else None
+    gpt_dim = latents[indices[0]].shape[1] if indices else 0
+    off = 0
+    for batch in batches:
+        nfr = [frames[i] for i in batch]
+        rows_n = sum(nfr)
+        parts = [latents[i] for i in batch]
+        if all(p.is_cuda for p in parts):
+            rows = parts[0] if len(parts) == 1 else torch.cat(parts, dim=0)           # one gather kernel
+        else:
+            rows = torch.empty(rows_n, gpt_dim, device=dev, dtype=parts[0].dtype)
+            r = 0
+            for p_, n in zip(parts, nfr):                                             # one cudaMemcpyAsync per segment
+                rows[r:r + n].copy_(p_, non_blocking=True)
+                r += n
+        out = flat[off * hop:(off + rows_n) * hop]
+        model.forward_ragged(rows, nfr, emb, pcm16=int16, out=out)
+        r = off
+        for i, n in zip(batch, nfr):
+            index[i] = (r * hop, n * hop)
+            r += n
+        if to_host:                                                                   # one async D2H per batch
+            ev = torch.cuda.Event()
+            ev.record(main)
+            copy_stream.wait_event(ev)
+            with torch.cuda.stream(copy_stream):
+                host[off * hop:(off + rows_n) * hop].copy_(out, non_blocking=True)
+        off += rows_n
+    done = None
+    if to_host:
+        done = torch.cuda.Event()
+        done.record(copy_stream)
+        flat.record_stream(copy_stream)
+    return ShardResult(flat=flat, host=host, index=index, done=done, batches=len(batches))
 
 
-def gather_waveforms(local: Dict[int, torch.Tensor], n_total: int, group=None) -> Optional[List[torch.Tensor]]:
-    """Host-side gather of per-rank results onto rank 0 (returns None elsewhere).
-    One variable-length `gather_object` -- never on the hot path."""
+@torch.no_grad()
+def decode_segments(model, latents: Sequence[Optional[torch.Tensor]], emb: torch.Tensor,
+                    indices: Optional[Sequence[int]] = None, max_batch_frames: int = 4096, max_batch: int = 64,
+                    to_host: bool = True, int16: bool = False) -> Dict[int, torch.Tensor]:
+    """`decode_shard` with the results split per segment: {segment index: waveform [T_i*hop]} (views of one
+    pinned host vector if `to_host`, of one device vector otherwise)."""
+    res = decode_shard(model, latents, emb, indices, max_batch_frames, max_batch, to_host, int16)
+    res.wait()
+    return {i: res.segment(i, on_host=to_host) for i in res.index}
+
+
+@torch.no_grad()
+def decode_sentences(model, latents: Sequence[torch.Tensor], cond_mel: torch.Tensor, max_batch_frames: int = 4096,
+                     max_batch: int = 64, cache_key=None) -> List[torch.Tensor]:
+    """Drop-in for the vocoder loop of `IndexTTS.infer_fast` (indextts/infer.py:439-463):
+
+        wavs = sched.decode_sentences(self.bigvgan, all_latents, auto_conditioning.transpose(1, 2))
+        wav = torch.cat(wavs, dim=1)                         # infer.py:473
+
+    `latents`: the per-sentence GPT latents [1, T_i, gpt_dim] in sentence order (infer.py:441),
+    `cond_mel`: the prompt mel [1, Tm, num_mels] (`auto_conditioning.transpose(1, 2)`).
+    Returns, in the same order, int16 waveforms [1, T_i*hop] on the host -- already
+    `clamp(32767 * wav, -32767, 32767)` (infer.py:462) and cast (infer.py:488, :492).  Sentences are decoded as a true
+    B > 1 ragged batch instead of being concatenated along time, so each one equals its stand-alone decode."""
+    emb = model.speaker_embedding(cond_mel, cache_key=cache_key)
+    segs = [l[0] if l.dim() == 3 else l for l in latents]
+    out = decode_segments(model, segs, emb, None, max_batch_frames, max_batch, to_host=True, int16=True)
+    return [out[i][None] for i in range(len(segs))]
+
+
+def gather_results(res: ShardResult, n_total: int, group=None, device: Optional[torch.device] = None):
+    """Gather every rank's flat result vector onto rank 0: returns the list of per-segment host tensors (views of
+    one pinned buffer) on rank 0, None elsewhere.  Traffic: one all_gather of a [n_total, 2] index table (who owns
+    what, where) and ONE gather of the flat vectors padded to the longest shard -- device to device over NCCL
+    (NVLink) followed by one device-to-host copy per shard on rank 0, or host tensors over gloo.  Never on the hot
+    path."""
     import torch.distributed as dist
 
-    if not dist.is_available() or not dist.is_initialized():
-        return [local[i] for i in range(n_total)]
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        res.wait()
+        return [res.segment(i) for i in range(n_total)]
     rank, world = dist.get_rank(group), dist.get_world_size(group)
-    payload = {i: w.cpu() for i, w in local.items()}
-    gathered = [None] * world if rank == 0 else None
-    dist.gather_object(payload, gathered, dst=0, group=group)
+    on_gpu = dist.get_backend(group) == "nccl"
+    dev = res.flat.device if on_gpu else torch.device("cpu")
+    table = torch.full((n_total, 2), -1, dtype=torch.int64)
+    for i, (off, n) in res.index.items():
+        table[i, 0], table[i, 1] = off, n
+    table = table.to(dev)
+    tables = [torch.empty_like(table) for _ in range(world)]
+    dist.all_gather(tables, table, group=group)
+    tables = [t.cpu() for t in tables]
+    sizes = [int(t[:, 1].clamp(min=0).sum()) for t in tables]
+    pad = max(sizes)
+    if on_gpu:
+        src = res.flat
+    else:
+        res.wait()
+        src = res.host if res.host is not None else res.flat.cpu()
+    mine = torch.zeros(pad, dtype=src.dtype, device=dev)
+    mine[: src.numel()].copy_(src)
+    parts = [torch.empty(pad, dtype=src.dtype, device=dev) for _ in range(world)] if rank == 0 else None
+    # byte views: gloo has no int16 collectives
+    dist.gather(mine.view(torch.uint8), [p_.view(torch.uint8) for p_ in parts] if rank == 0 else None, dst=0, group=group)
     if rank != 0:
         return None
-    merged: Dict[int, torch.Tensor] = {}
-    for part in gathered:
-        merged.update(part)
-    missing = [i for i in range(n_total) if i not in merged]
+    host = torch.empty(world, pad, dtype=src.dtype, pin_memory=torch.cuda.is_available())
+    for r in range(world):
+        host[r].copy_(parts[r], non_blocking=on_gpu)
+    if on_gpu:
+        torch.cuda.current_stream(dev).synchronize()
+    out: List[Optional[torch.Tensor]] = [None] * n_total
+    for r, t in enumerate(tables):
+        for i in torch.nonzero(t[:, 1] >= 0).flatten().tolist():
+            off, n = int(t[i, 0]), int(t[i, 1])
+            out[i] = host[r, off:off + n]
+    missing = [i for i, w in enumerate(out) if w is None]
     if missing:
-        raise RuntimeError(f"gather_waveforms: segments {missing[:8]} were decoded by no rank")
-    return [merged[i] for i in range(n_total)]
+        raise RuntimeError(f"gather_results: segments {missing[:8]} were decoded by no rank")
+    return out

@@ -60,9 +60,12 @@ __device__ __forceinline__ void mma16816_f16(float (&c)[4], const uint32_t (&a)[
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+// saturating (F2FP.SATFINITE, same cost): an activated sample beyond fp16's range (tiny beta) becomes +-65504 instead of
+// inf, which the symmetric down-FIR taps would turn into NaN across the output
 __device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
-  __half2 h = __floats2half2_rn(lo, hi);
-  return *reinterpret_cast<uint32_t*>(&h);
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
 }
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
@@ -276,7 +279,11 @@ cudaError_t launch_act_c8_mma(const ActArgs& a, cudaStream_t s) {
   const int nitems = ((ntiles + GT - 1) / GT) * nchunks;
   dim3 grid((nitems + 2 * WPB - 1) / (2 * WPB), 1, a.B), block(WPB * 32);
   const size_t smem = (size_t)WPB * 2 * XROWS * 16;
-  static bool attr_done = false;
+  static bool attr_done_dev[64] = {false};   // the attribute is per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+  bool& attr_done = attr_done_dev[dev];
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(act1d_c8_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(act1d_c8_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -55,7 +55,8 @@ struct ConvLayer {
       ntaps = k; N = Cout; u = 1; p = 0; q_extra = 0;
       for (int j = 0; j < k; ++j) tap_off[j] = (j - (k - 1) / 2) * d;
     } else {
-      ntaps = k / u; N = u * Cout; p = (k - u) / 2; q_extra = p > 0 ? 1 : 0;
+      // output row q*u + phi - p: the last p rows of a segment need q up to len_in + ceil(p/u) - 1
+      ntaps = k / u; N = u * Cout; p = (k - u) / 2; q_extra = (p + u - 1) / u;
       for (int m = 0; m < ntaps; ++m) tap_off[m] = -m;
     }
   }
@@ -105,7 +106,13 @@ struct bvg_handle {
   std::map<std::string, ParamSlot> ecapa_params;
   bool ecapa_ready = false;
   std::vector<void*> owned;
-  std::map<const void*, uint64_t> ws_owner;   // workspace -> uid of the plan whose guard rows it holds
+  // Plan tables (segment descriptors, tile prefix sums) live in a handle-owned arena: device memory plus a pinned
+  // host mirror, carved into slices that are recycled through per-size free lists.  Creating a plan therefore costs
+  // no cudaMalloc and no synchronous copy once the arena is warm (ragged SRT batches make a new plan per batch).
+  struct TableChunk { char* dev; char* host; size_t cap, used; };
+  std::vector<TableChunk> tab_chunks;
+  std::map<size_t, std::vector<std::pair<char*, char*>>> tab_free;   // slice bytes -> (device, host) slices
+  int64_t plans_created = 0;
   bool finalized = false;
   int launch_counter = 0;   // kernel launches issued by the forward in progress
   // optional per-launch CUDA-event timing (bench.py's roofline numbers)
@@ -149,6 +156,10 @@ struct bvg_plan {
   std::vector<long long> sumlen;   // valid rows over all segments, per geometry
   SegDesc* seg_dev = nullptr;   // [(nups+1)][B]
   int* prefix_dev = nullptr;    // m-tile prefix tables [g][msub in 1,2,4][q_extra][B+1]
+  int* latrow_dev = nullptr;    // [B+1] prefix sum of frames (ragged latent / waveform I/O)
+  char *tab_dev = nullptr, *tab_host = nullptr;   // one slice of the handle's table arena holds all three
+  size_t tab_bytes = 0;
+  bool tab_uploaded = false;    // the first forward copies the slice to the device on ITS stream
   std::vector<int> total_mt;    // [g][msub in 1,2,4][q_extra]
   size_t ws_bytes = 0;
   size_t off_lat = 0, off_pre = 0, off_bias = 0;
@@ -164,6 +175,21 @@ namespace {
 int dev_alloc(bvg_handle* h, void** p, size_t bytes) {
   CK(cudaMalloc(p, bytes ? bytes : 4));
   h->owned.push_back(*p);
+  return 0;
+}
+
+int table_slice(bvg_handle* h, size_t bytes, char** dev, char** host) {
+  auto& fl = h->tab_free[bytes];
+  if (!fl.empty()) { *dev = fl.back().first; *host = fl.back().second; fl.pop_back(); return 0; }
+  if (h->tab_chunks.empty() || h->tab_chunks.back().used + bytes > h->tab_chunks.back().cap) {
+    bvg_handle::TableChunk c{nullptr, nullptr, bytes > ((size_t)1 << 20) ? bytes : ((size_t)1 << 20), 0};
+    CK(cudaMalloc((void**)&c.dev, c.cap));
+    if (cudaMallocHost((void**)&c.host, c.cap) != cudaSuccess) { cudaFree(c.dev); return fail("table arena: pinned allocation failed"); }
+    h->tab_chunks.push_back(c);
+  }
+  auto& c = h->tab_chunks.back();
+  *dev = c.dev + c.used; *host = c.host + c.used;
+  c.used += bytes;
   return 0;
 }
 
@@ -307,7 +333,10 @@ int bvg_create(const bvg_config* cfg, bvg_handle** out) {
   int ch = C0;
   for (int i = 0; i < nups; ++i) {
     const int u = cfg->upsample_rates[i], k = cfg->upsample_kernel_sizes[i];
-    if (k % u || (k - u) % 2) { delete h; return fail("bvg_create: upsample (k=%d,u=%d) unsupported", k, u); }
+    if (u < 1 || k % u || (k - u) % 2 || k / u > BVG_MAX_TAPS || (k - u) / 2 > 8 * u) {
+      delete h;
+      return fail("bvg_create: upsample (k=%d,u=%d) unsupported (need k %% u == 0, k - u even, k/u <= %d taps)", k, u, BVG_MAX_TAPS);
+    }
     h->hop *= u;
     ConvLayer& U = h->ups[i];
     U.transposed = true; U.Cin = ch; U.Cout = ch / 2; U.k = k; U.u = u; U.setup();
@@ -366,6 +395,7 @@ int bvg_create(const bvg_config* cfg, bvg_handle** out) {
 void bvg_destroy(bvg_handle* h) {
   if (!h) return;
   for (void* p : h->owned) cudaFree(p);
+  for (auto& c : h->tab_chunks) { cudaFree(c.dev); cudaFreeHost(c.host); }
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   delete h;
 }
@@ -527,29 +557,36 @@ int bvg_plan_create(bvg_handle* h, int32_t B, const int32_t* frames, int32_t mod
     p->maxlen[g] = mx;
   }
   p->max_frames = p->maxlen[0];
-  if (cudaMalloc(&p->seg_dev, seg.size() * sizeof(SegDesc)) != cudaSuccess ||
-      cudaMemcpy(p->seg_dev, seg.data(), seg.size() * sizeof(SegDesc), cudaMemcpyHostToDevice) != cudaSuccess) {
-    delete p;
-    return fail("bvg_plan_create: segment table upload failed");
-  }
   {
-    std::vector<int> pref((size_t)ng * 6 * (B + 1));
+    // one table slice: [SegDesc ng*B][tile prefix ng*6*(B+1)][latent row prefix B+1]
+    const size_t seg_bytes = align_up(seg.size() * sizeof(SegDesc), 16);
+    const size_t pref_n = (size_t)ng * 6 * (B + 1);
+    const size_t pref_bytes = align_up(pref_n * sizeof(int), 16);
+    p->tab_bytes = align_up(seg_bytes + pref_bytes + (size_t)(B + 1) * sizeof(int), 1024);
+    if (table_slice(h, p->tab_bytes, &p->tab_dev, &p->tab_host)) { delete p; return 1; }
+    memcpy(p->tab_host, seg.data(), seg.size() * sizeof(SegDesc));
+    int* pref = reinterpret_cast<int*>(p->tab_host + seg_bytes);
     p->total_mt.assign((size_t)ng * 6, 0);
     for (int g = 0; g < ng; ++g)
       for (int mi = 0; mi < 3; ++mi)
         for (int qe = 0; qe < 2; ++qe) {
           const int ms = 1 << mi;   // 128-row sub-tiles per tile: 1, 2, 4
           const int ti = (g * 3 + mi) * 2 + qe;
-          int* pf = pref.data() + (size_t)ti * (B + 1);
+          // slot 1: extra q rows of the up-convolution that reads this geometry (the only transposed layer that does)
+          const int qx = (qe && g < h->nups) ? h->ups[g].q_extra : 0;
+          int* pf = pref + (size_t)ti * (B + 1);
           pf[0] = 0;
-          for (int b = 0; b < B; ++b) pf[b + 1] = pf[b] + (seg[(size_t)g * B + b].len + qe + 128 * ms - 1) / (128 * ms);
+          for (int b = 0; b < B; ++b) pf[b + 1] = pf[b] + (seg[(size_t)g * B + b].len + qx + 128 * ms - 1) / (128 * ms);
           p->total_mt[ti] = pf[B];
         }
-    if (cudaMalloc(&p->prefix_dev, pref.size() * sizeof(int)) != cudaSuccess ||
-        cudaMemcpy(p->prefix_dev, pref.data(), pref.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) {
-      delete p;
-      return fail("bvg_plan_create: tile table upload failed");
-    }
+    int* lr = reinterpret_cast<int*>(p->tab_host + seg_bytes + pref_bytes);
+    lr[0] = 0;
+    for (int b = 0; b < B; ++b) lr[b + 1] = lr[b] + frames[b];
+    p->seg_dev = reinterpret_cast<SegDesc*>(p->tab_dev);
+    p->prefix_dev = reinterpret_cast<int*>(p->tab_dev + seg_bytes);
+    p->latrow_dev = reinterpret_cast<int*>(p->tab_dev + seg_bytes + pref_bytes);
+    p->tab_uploaded = false;
+    ++h->plans_created;
   }
   // workspace carve-up
   size_t off = 0;
@@ -569,23 +606,33 @@ int bvg_plan_create(bvg_handle* h, int32_t B, const int32_t* frames, int32_t mod
   p->bias_stride = bo;
   p->off_bias = take((size_t)B * bo * sizeof(float));
   p->ws_bytes = off;
-  p->num_launches = 1 + ng + 1 + h->nups * (1 + h->nk * h->nd * 4) + 2;
+  p->num_launches = 1 + 1 + ng + 1 + h->nups * (1 + h->nk * h->nd * 4) + 2;
   *out = p;
   return 0;
 }
 
 void bvg_plan_destroy(bvg_plan* p) {
   if (!p) return;
-  if (p->seg_dev) cudaFree(p->seg_dev);
-  if (p->prefix_dev) cudaFree(p->prefix_dev);
+  if (p->tab_dev) p->h->tab_free[p->tab_bytes].push_back({p->tab_dev, p->tab_host});   // recycle the table slice
   delete p;
 }
+int64_t bvg_plans_created(const bvg_handle* h) { return h ? h->plans_created : 0; }
+int64_t bvg_plan_total_frames(const bvg_plan* p) { return p ? (int64_t)p->sumlen[0] : 0; }
 size_t bvg_plan_workspace_bytes(const bvg_plan* p) { return p ? p->ws_bytes : 0; }
 int32_t bvg_plan_max_frames(const bvg_plan* p) { return p ? p->max_frames : 0; }
 int32_t bvg_plan_num_launches(const bvg_plan* p) { return p ? p->num_launches : 0; }
 
 static int forward_impl(bvg_handle* h, bvg_plan* p, const void* latent, int32_t latent_dtype, const float* spk_emb,
-                        int32_t spk_batch, float* wav, int16_t* pcm, void* workspace, size_t workspace_bytes, void* stream);
+                        int32_t spk_batch, float* wav, int16_t* pcm, void* workspace, size_t workspace_bytes, void* stream,
+                        bool ragged = false);
+
+int bvg_forward_ragged(bvg_handle* h, bvg_plan* p, const void* latent_rows, int32_t latent_dtype, const float* spk_emb,
+                       int32_t spk_batch, float* wav_rows_or_null, int16_t* pcm_rows_or_null, void* workspace,
+                       size_t workspace_bytes, void* stream) {
+  if (!wav_rows_or_null && !pcm_rows_or_null) return fail("bvg_forward_ragged: no output buffer");
+  return forward_impl(h, p, latent_rows, latent_dtype, spk_emb, spk_batch, wav_rows_or_null, pcm_rows_or_null, workspace,
+                      workspace_bytes, stream, true);
+}
 
 int bvg_forward(bvg_handle* h, bvg_plan* p, const void* latent, int32_t latent_dtype, const float* spk_emb,
                 int32_t spk_batch, float* wav, void* workspace, size_t workspace_bytes, void* stream) {
@@ -601,7 +648,8 @@ int bvg_forward_pcm16(bvg_handle* h, bvg_plan* p, const void* latent, int32_t la
 }
 
 static int forward_impl(bvg_handle* h, bvg_plan* p, const void* latent, int32_t latent_dtype, const float* spk_emb,
-                        int32_t spk_batch, float* wav, int16_t* pcm, void* workspace, size_t workspace_bytes, void* stream) {
+                        int32_t spk_batch, float* wav, int16_t* pcm, void* workspace, size_t workspace_bytes, void* stream,
+                        bool ragged) {
   if (!h || !p || !latent || !spk_emb || !workspace) return fail("bvg_forward: null argument");
   if (!h->finalized) return fail("bvg_forward: call bvg_finalize first");
   if (p->h != h) return fail("bvg_forward: plan belongs to another handle");
@@ -611,28 +659,34 @@ static int forward_impl(bvg_handle* h, bvg_plan* p, const void* latent, int32_t 
   cudaStream_t s = (cudaStream_t)stream;
   char* ws = (char*)workspace;
   const int B = p->B, ng = h->nups + 1, dt = p->dtype;
-  // Guard rows (between / around segments) must read as zero.  Kernels never write them, so they
-  // are cleared only when this workspace was last laid out for a different plan.
+  // plan tables: pinned host mirror -> device slice, once, ordered on this stream (no allocation, no host sync)
+  if (!p->tab_uploaded) {
+    CK(cudaMemcpyAsync(p->tab_dev, p->tab_host, p->tab_bytes, cudaMemcpyHostToDevice, s));
+    p->tab_uploaded = true;
+  }
+  // Guard rows (between / around segments) must read as zero.  Kernels never write them, but the workspace may have
+  // been laid out for another plan (or be a recycled allocation) since: one launch re-clears the guard rows of all
+  // 2 + 5 * nups buffers on every forward (a few hundred KB of stores).
   {
-    auto it = h->ws_owner.find(workspace);
-    if (it == h->ws_owner.end() || it->second != p->uid) {
-      CK(launch_zero_guards(ws + p->off_lat, p->esize, p->seg_dev, B, h->cfg.gpt_dim, p->R[0], s));
-      CK(launch_zero_guards(ws + p->off_pre, p->esize, p->seg_dev, B, p->C[0], p->R[0], s));
-      for (int g = 1; g < ng; ++g) {
-        const SegDesc* sg = p->seg_dev + (size_t)g * B;
-        const size_t offs[5] = {p->off_U[g], p->off_X[g], p->off_A[g], p->off_Y[g], p->off_XS[g]};
-        for (size_t o : offs) CK(launch_zero_guards(ws + o, p->esize, sg, B, p->C[g], p->R[g], s));
-      }
-      h->ws_owner[workspace] = p->uid;
-    }
+    GuardJobs jobs{};
+    auto add = [&](size_t off, int g, int C) {
+      jobs.job[jobs.n++] = GuardJob{ws + off, p->seg_dev + (size_t)g * B, C >> 3, p->R[g], p->esize == 4 ? 2 : 1};
+    };
+    add(p->off_lat, 0, h->cfg.gpt_dim);
+    add(p->off_pre, 0, p->C[0]);
+    for (int g = 1; g < ng; ++g)
+      for (size_t o : {p->off_U[g], p->off_X[g], p->off_A[g], p->off_Y[g], p->off_XS[g]}) add(o, g, p->C[g]);
+    ProfScope ps(h, s, PROF_OTHER, 0.0, 0.0);
+    CK(launch_zero_guards_all(jobs, B, s));
   }
   const SegDesc* seg0 = p->seg_dev;
-  h->launch_counter = 1 + ng + 1;   // pack + cond biases + conv_post (the helpers below count their own)
+  h->launch_counter = 1 + 1 + ng + 1;   // guards + pack + cond biases + conv_post (the helpers below count their own)
   float* biasb = (float*)(ws + p->off_bias);
   const int D = h->cfg.speaker_embedding_dim;
   {
   ProfScope ps(h, s, PROF_OTHER, 0.0, (double)h->cfg.gpt_dim * p->sumlen[0] * (4.0 + p->esize));
-  CK(launch_pack_latent(latent, latent_dtype, ws + p->off_lat, dt, seg0, B, p->max_frames, h->cfg.gpt_dim, p->R[0], s));
+  CK(launch_pack_latent(latent, latent_dtype, ws + p->off_lat, dt, seg0, ragged ? p->latrow_dev : nullptr, B, p->max_frames,
+                        h->cfg.gpt_dim, p->R[0], s));
   // speaker conditioning folded into per-segment biases
   CK(launch_cond_bias(h->conv_pre.bias, h->cond_pre.w, h->cond_pre.b, spk_emb, biasb + p->bias_off[0], p->C[0], D, B,
                       spk_batch, p->bias_stride, s));
@@ -675,8 +729,8 @@ static int forward_impl(bvg_handle* h, bvg_plan* p, const void* latent, int32_t 
     const SegDesc* seg = p->seg_dev + (size_t)g * B;
     if (run_act(h->act_post, p, g, stage_in, ws + p->off_A[g], s)) return 1;
     ProfScope ps(h, s, PROF_OTHER, 0.0, ((double)p->C[g] * p->esize + 4.0) * (double)p->sumlen[g]);
-    CK(launch_conv_post_tanh(ws + p->off_A[g], dt, h->conv_post.w_raw, h->conv_post.bias, wav, (short*)pcm, seg, B, p->C[g], p->R[g],
-                             p->max_frames * h->hop, s));
+    CK(launch_conv_post_tanh(ws + p->off_A[g], dt, h->conv_post.w_raw, h->conv_post.bias, wav, (short*)pcm, seg,
+                             ragged ? p->latrow_dev : nullptr, h->hop, B, p->C[g], p->R[g], p->max_frames * h->hop, s));
   }
   p->num_launches = h->launch_counter;   // what this forward actually issued (fused layers launch once)
   return 0;
@@ -703,12 +757,6 @@ int bvg_profile_read(bvg_handle* h, double* ms, double* flops, double* bytes, in
   }
   h->prof.clear();
   h->ev_used = 0;
-  return 0;
-}
-
-int bvg_workspace_reset(bvg_handle* h) {
-  if (!h) return fail("bvg_workspace_reset: null handle");
-  h->ws_owner.clear();
   return 0;
 }
 
@@ -764,7 +812,8 @@ int conv_op(bool transposed, const float* x, const float* w, const float* bias, 
   if (bvg_device_check()) return 1;
   if (!x || !w || !y) return fail("conv op: null argument");
   if (Cin % 8 || Cout % 8) return fail("conv op: Cin and Cout must be multiples of 8");
-  if (k < 1 || (!transposed && (k > BVG_MAX_TAPS || !(k & 1))) || (transposed && (k % u || (k - u) % 2)))
+  if (k < 1 || u < 1 || (!transposed && (k > BVG_MAX_TAPS || !(k & 1))) ||
+      (transposed && (k % u || (k - u) % 2 || k / u > BVG_MAX_TAPS || (k - u) / 2 > 8 * u)))
     return fail("conv op: unsupported kernel size");
   ConvLayer L;
   L.transposed = transposed; L.Cin = Cin; L.Cout = Cout; L.k = k; L.d = d; L.u = u; L.setup();

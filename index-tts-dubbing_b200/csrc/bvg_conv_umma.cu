@@ -242,9 +242,10 @@ __device__ __forceinline__ void wmma_f16(float (&c)[4], const uint32_t (&a)[4], 
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
-__device__ __forceinline__ uint32_t pk_f16(float lo, float hi) {
-  __half2 h = __floats2half2_rn(lo, hi);
-  return *reinterpret_cast<uint32_t*>(&h);
+__device__ __forceinline__ uint32_t pk_f16(float lo, float hi) {   // saturating, see bvg_act3.cu
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
 }
 __device__ __forceinline__ uint32_t pk_bf16(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
@@ -1145,16 +1146,22 @@ cudaError_t launch_conv_umma(const ConvArgs& a, cudaStream_t s) {
   if (fuse ? !configure_fused(a, a.msub, ka, smem) : !configure(a, a.msub, ka, smem)) return cudaErrorInvalidValue;
   ka.tile_prefix = a.tile_prefix;
   ka.total_mt = a.total_mt;
-  static int num_sms = 0;
-  if (!num_sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+  // per-device one-shot state: MaxDynamicSharedMemorySize is a per-device function attribute and the grid is
+  // sized from the device's own SM count (a process may drive several GPUs)
+  static int sms_of_dev[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+  if (!sms_of_dev[dev]) {
+    int n = 0;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_umma_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX);
-    if (e != cudaSuccess) { num_sms = 0; return e; }
+    if (e != cudaSuccess) return e;
+    sms_of_dev[dev] = n;
   }
+  const int num_sms = sms_of_dev[dev];
   static const int trace_cin = env_int("BVG_CONV_TRACE", 0);   // e.g. 24: trace the first k=3 conv with Cin == 24
   static bool traced = false;
   static const int trace_taps = env_int("BVG_CONV_TRACE_TAPS", 3);

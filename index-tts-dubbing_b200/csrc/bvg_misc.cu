@@ -5,10 +5,11 @@
 
 namespace {
 
-// latent [B, Tmax, C] row-major (any float type)  ->  packed c8 [C/8][R][8]
+// latent [B, Tmax, C] row-major (any float type)  ->  packed c8 [C/8][R][8].
+// src_row != nullptr: ragged source -- segment b's frames are rows src_row[b] .. src_row[b] + len of one [sum len, C] matrix
 template <typename TI, typename TO>
 __global__ void pack_latent_kernel(const TI* __restrict__ x, TO* __restrict__ y, const SegDesc* __restrict__ seg,
-                                   int B, int Tmax, int C, int R) {
+                                   const int* __restrict__ src_row, int B, int Tmax, int C, int R) {
   const int nch = C >> 3;
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t total = (size_t)B * Tmax * nch;
@@ -18,7 +19,7 @@ __global__ void pack_latent_kernel(const TI* __restrict__ x, TO* __restrict__ y,
   int t = bt % Tmax, b = bt / Tmax;
   SegDesc sd = seg[b];
   if (t >= sd.len) return;
-  const TI* p = x + ((size_t)b * Tmax + t) * C + chunk * 8;
+  const TI* p = x + ((src_row ? (size_t)src_row[b] : (size_t)b * Tmax) + t) * C + chunk * 8;
   Vec8<TO> v;
 #pragma unroll
   for (int c = 0; c < 8; ++c) v.v[c] = to_f32(p[c]);
@@ -72,7 +73,7 @@ __global__ void cond_bias_kernel(const float* __restrict__ bias, const float* __
 template <typename T>
 __global__ void conv_post_tanh_kernel(const T* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                                       float* __restrict__ wav, short* __restrict__ pcm, const SegDesc* __restrict__ seg,
-                                      int C, int R, int Lmax) {
+                                      const int* __restrict__ dst_row, int hop, int C, int R, int Lmax) {
   __shared__ float ws[7][64];
   for (int i = threadIdx.x; i < 7 * C; i += blockDim.x) {
     int j = i / C, c = i - j * C;
@@ -99,10 +100,17 @@ __global__ void conv_post_tanh_kernel(const T* __restrict__ x, const float* __re
     }
     out = tanhf(acc);
   }
-  if (wav) wav[(size_t)b * Lmax + t] = out;
+  // dense output [B][Lmax] (zeros beyond a segment's length) or, with dst_row, ragged: segment b's samples start at
+  // dst_row[b] * hop of one [sum len] vector and nothing is written beyond its length
+  size_t o = (size_t)b * Lmax + t;
+  if (dst_row) {
+    if (t >= sd.len) return;
+    o = (size_t)dst_row[b] * hop + t;
+  }
+  if (wav) wav[o] = out;
   // 16-bit PCM as the reference's callers produce it: clamp(32767 * wav, -32767, 32767) then a truncating
   // cast (infer.py:462, :627, :650)
-  if (pcm) pcm[(size_t)b * Lmax + t] = (short)__float2int_rz(fminf(fmaxf(__fmul_rn(32767.f, out), -32767.f), 32767.f));
+  if (pcm) pcm[o] = (short)__float2int_rz(fminf(fmaxf(__fmul_rn(32767.f, out), -32767.f), 32767.f));
 }
 
 // Conv1d weight [Cout][Cin][k] -> [k][Cin][Cout]
@@ -150,16 +158,31 @@ __global__ void zero_guards_kernel(uint4* __restrict__ buf, const SegDesc* __res
   for (int i = threadIdx.x; i < n; i += blockDim.x) p[i] = z;
 }
 
+// All buffers of a plan in ONE launch: block = (gap, chunk counted across the buffers).
+__global__ void zero_guards_all_kernel(const GuardJobs jobs, int B) {
+  const int g = blockIdx.x;
+  int chunk = blockIdx.y, j = 0;
+  while (chunk >= jobs.job[j].chunks) { chunk -= jobs.job[j].chunks; ++j; }
+  const GuardJob jb = jobs.job[j];
+  const SegDesc* seg = jb.seg;
+  const int lo = g == 0 ? 0 : seg[g - 1].off + seg[g - 1].len;
+  const int hi = g == B ? jb.R : seg[g].off;
+  uint4* p = reinterpret_cast<uint4*>(jb.buf) + ((size_t)chunk * jb.R + lo) * jb.vec_per_row;
+  const int n = (hi - lo) * jb.vec_per_row;
+  const uint4 z = make_uint4(0, 0, 0, 0);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) p[i] = z;
+}
+
 inline int nblk(size_t n, int t) { return (int)((n + t - 1) / t); }
 
 }  // namespace
 
-cudaError_t launch_pack_latent(const void* x, int in_dtype, void* y, int out_dtype, const SegDesc* seg, int B,
-                               int Tmax, int C, int R, cudaStream_t s) {
+cudaError_t launch_pack_latent(const void* x, int in_dtype, void* y, int out_dtype, const SegDesc* seg,
+                               const int* src_row, int B, int Tmax, int C, int R, cudaStream_t s) {
   size_t total = (size_t)B * Tmax * (C >> 3);
   if (!total) return cudaSuccess;
   dim3 g(nblk(total, 256)), blk(256);
-#define PL(TI, TO) pack_latent_kernel<TI, TO><<<g, blk, 0, s>>>((const TI*)x, (TO*)y, seg, B, Tmax, C, R)
+#define PL(TI, TO) pack_latent_kernel<TI, TO><<<g, blk, 0, s>>>((const TI*)x, (TO*)y, seg, src_row, B, Tmax, C, R)
   if (out_dtype == 0) {
     if (in_dtype == 0) PL(float, float); else if (in_dtype == 1) PL(__nv_bfloat16, float); else PL(__half, float);
   } else {
@@ -195,11 +218,21 @@ cudaError_t launch_cond_bias(const float* bias, const float* cw, const float* cb
 }
 
 cudaError_t launch_conv_post_tanh(const void* x, int dtype, const float* w, const float* bias, float* wav, short* pcm,
-                                  const SegDesc* seg, int B, int C, int R, int Lmax, cudaStream_t s) {
+                                  const SegDesc* seg, const int* dst_row, int hop, int B, int C, int R, int Lmax,
+                                  cudaStream_t s) {
   if (B <= 0 || Lmax <= 0) return cudaSuccess;
   dim3 g(nblk(Lmax, 256), B), blk(256);
-  if (dtype == 0) conv_post_tanh_kernel<float><<<g, blk, 0, s>>>((const float*)x, w, bias, wav, pcm, seg, C, R, Lmax);
-  else conv_post_tanh_kernel<__nv_bfloat16><<<g, blk, 0, s>>>((const __nv_bfloat16*)x, w, bias, wav, pcm, seg, C, R, Lmax);
+  if (dtype == 0) conv_post_tanh_kernel<float><<<g, blk, 0, s>>>((const float*)x, w, bias, wav, pcm, seg, dst_row, hop, C, R, Lmax);
+  else conv_post_tanh_kernel<__nv_bfloat16><<<g, blk, 0, s>>>((const __nv_bfloat16*)x, w, bias, wav, pcm, seg, dst_row, hop, C, R, Lmax);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_zero_guards_all(const GuardJobs& jobs, int B, cudaStream_t s) {
+  int chunks = 0;
+  for (int j = 0; j < jobs.n; ++j) chunks += jobs.job[j].chunks;
+  if (!chunks) return cudaSuccess;
+  dim3 g(B + 1, chunks);
+  zero_guards_all_kernel<<<g, 128, 0, s>>>(jobs, B);
   return cudaGetLastError();
 }
 

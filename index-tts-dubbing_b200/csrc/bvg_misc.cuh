@@ -1,8 +1,8 @@
 #pragma once
 #include "bvg_common.cuh"
 
-cudaError_t launch_pack_latent(const void* x, int in_dtype, void* y, int out_dtype, const SegDesc* seg, int B,
-                               int Tmax, int C, int R, cudaStream_t s);
+cudaError_t launch_pack_latent(const void* x, int in_dtype, void* y, int out_dtype, const SegDesc* seg,
+                               const int* src_row, int B, int Tmax, int C, int R, cudaStream_t s);
 cudaError_t launch_nct_to_c8(const float* x, void* y, int out_dtype, const SegDesc* seg, int B, int C, int T, int R,
                              cudaStream_t s);
 cudaError_t launch_c8_to_nct(const void* x, int in_dtype, float* y, const SegDesc* seg, int B, int C, int T, int R,
@@ -10,7 +10,8 @@ cudaError_t launch_c8_to_nct(const void* x, int in_dtype, float* y, const SegDes
 cudaError_t launch_cond_bias(const float* bias, const float* cw, const float* cb, const float* spk, float* out, int C,
                              int D, int B, int spkB, int out_bstride, cudaStream_t s);
 cudaError_t launch_conv_post_tanh(const void* x, int dtype, const float* w, const float* bias, float* wav, short* pcm,
-                                  const SegDesc* seg, int B, int C, int R, int Lmax, cudaStream_t s);
+                                  const SegDesc* seg, const int* dst_row, int hop, int B, int C, int R, int Lmax,
+                                  cudaStream_t s);
 cudaError_t launch_repack_conv(const float* w, float* wp, int Cout, int Cin, int k, cudaStream_t s);
 cudaError_t launch_repack_convt(const float* w, float* wp, int Cin, int Cout, int k, int u, cudaStream_t s);
 cudaError_t launch_snake_params(const float* la, const float* lb, float* alpha, float* inv_beta, int n,
@@ -19,3 +20,7 @@ cudaError_t launch_snake_params(const float* la, const float* lb, float* alpha, 
 size_t umma_weight_image_bytes(int ntaps, int Cin, int N);
 cudaError_t launch_repack_umma(const float* wp_tap_major, void* img, int ntaps, int Cin, int N, float acc_img_scale, cudaStream_t s);
 cudaError_t launch_zero_guards(void* buf, int esize, const SegDesc* seg, int B, int C, int R, cudaStream_t s);
+// every packed buffer of a plan in one launch
+struct GuardJob { void* buf; const SegDesc* seg; int chunks, R, vec_per_row; };
+struct GuardJobs { GuardJob job[2 + 5 * 8]; int n; };
+cudaError_t launch_zero_guards_all(const GuardJobs& jobs, int B, cudaStream_t s);

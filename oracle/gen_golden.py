@@ -54,8 +54,31 @@ def ref_generator(models, sd_np, dtype=torch.float32):
     return g.to(dtype)
 
 
+def prompt_mel():
+    """Config 1's speaker input: the mel of the reference's own tests/sample_prompt.wav with the semantics of
+    indextts/infer.py:509-514 (mean over channels, torchaudio Resample -> 24 kHz, MelSpectrogramFeatures).
+    torchaudio.load needs torchcodec here, so the wav is read with scipy and scaled like torchaudio does
+    for int16 PCM (/ 32768).  Returns (audio24k [1,N] fp32, mel [1,Tm,100] fp32, already transposed the way
+    infer.py:458 passes it: auto_conditioning.transpose(1, 2))."""
+    import scipy.io.wavfile as wavfile
+    import torchaudio
+    sys.path.insert(0, REF_ROOT)
+    from indextts.utils.feature_extractors import MelSpectrogramFeatures
+    sr, a = wavfile.read(os.path.join(REF_ROOT, "tests", "sample_prompt.wav"))
+    audio = torch.from_numpy(a.astype(np.float32) / 32768.0).t()
+    audio = torch.mean(audio, dim=0, keepdim=True)
+    audio = torchaudio.transforms.Resample(sr, 24000)(audio)
+    mel = MelSpectrogramFeatures()(audio)                     # [1, 100, Tm]
+    return audio.numpy(), mel.transpose(1, 2).contiguous().numpy()
+
+
 def main():
+    """`python oracle/gen_golden.py` regenerates everything; `python oracle/gen_golden.py cfg1 prompt` only the
+    named groups (taps, act, amp, ecapa, tiny, cfg1, prompt, logmel).  A full run reproduces the committed files
+    (one torch seed, fixed order); a partial run only touches the named ones (their inputs do not depend on
+    the torch random stream)."""
     from b200vgan import synth
+    only = sys.argv[1:]
     torch.set_grad_enabled(False)
     torch.manual_seed(0)
     models = import_reference()
@@ -64,85 +87,108 @@ def main():
     from indextts.BigVGAN import activations
     os.makedirs(GOLD, exist_ok=True)
 
+    def want(name):
+        return not only or name in only
+
     # 1. filter taps ------------------------------------------------------------------
-    taps = kaiser_sinc_filter1d(0.25, 0.3, 12).reshape(-1).numpy()
-    np.savez(os.path.join(GOLD, "kaiser_taps.npz"), taps=taps)
+    if want("taps"):
+        taps = kaiser_sinc_filter1d(0.25, 0.3, 12).reshape(-1).numpy()
+        np.savez(os.path.join(GOLD, "kaiser_taps.npz"), taps=taps)
 
     # 2. Activation1d(SnakeBeta, logscale) ---------------------------------------------
-    rng = np.random.default_rng(11)
-    cases = {}
-    for name, (B, C, L) in {"a": (2, 16, 50), "b": (1, 8, 1), "c": (1, 24, 7), "d": (3, 8, 301)}.items():
-        x = (1.5 * rng.standard_normal((B, C, L))).astype(np.float32)
-        la = (0.5 * rng.standard_normal(C)).astype(np.float32)
-        lb = (0.5 * rng.standard_normal(C)).astype(np.float32)
-        act = Activation1d(activation=activations.SnakeBeta(C, alpha_logscale=True))
-        act.act.alpha.data = torch.from_numpy(la)
-        act.act.beta.data = torch.from_numpy(lb)
-        y = act(torch.from_numpy(x)).numpy()
-        cases.update({f"{name}_x": x, f"{name}_alpha": la, f"{name}_beta": lb, f"{name}_y": y})
-    np.savez(os.path.join(GOLD, "activation1d.npz"), **cases)
+    if want("act"):
+        rng = np.random.default_rng(11)
+        cases = {}
+        for name, (B, C, L) in {"a": (2, 16, 50), "b": (1, 8, 1), "c": (1, 24, 7), "d": (3, 8, 301)}.items():
+            x = (1.5 * rng.standard_normal((B, C, L))).astype(np.float32)
+            la = (0.5 * rng.standard_normal(C)).astype(np.float32)
+            lb = (0.5 * rng.standard_normal(C)).astype(np.float32)
+            act = Activation1d(activation=activations.SnakeBeta(C, alpha_logscale=True))
+            act.act.alpha.data = torch.from_numpy(la)
+            act.act.beta.data = torch.from_numpy(lb)
+            y = act(torch.from_numpy(x)).numpy()
+            cases.update({f"{name}_x": x, f"{name}_alpha": la, f"{name}_beta": lb, f"{name}_y": y})
+        np.savez(os.path.join(GOLD, "activation1d.npz"), **cases)
 
-    # 3. AMPBlock1 at a small width (reference class, own synthetic weights) -------------
-    h = H(yaml.safe_load(open(f"{REF_ROOT}/checkpoints/config.yaml"))["bigvgan"])
-    h["use_cuda_kernel"] = False
-    amp = {}
-    for ks in (3, 7, 11):
-        C, L = 16, 160
-        blk = models.AMPBlock1(h, C, ks, (1, 3, 5), activation="snakebeta")
-        blk.remove_weight_norm()
-        blk.eval()
-        sd = {k: ((0.8 / (C * ks) ** 0.5) * torch.randn_like(v) if v.ndim == 3 and v.shape[-1] != 12 else
-                  (0.5 * torch.randn_like(v) if "act." in k else
-                   (0.1 * torch.randn_like(v) if k.endswith("bias") else v)))
-              for k, v in blk.state_dict().items()}
-        blk.load_state_dict(sd)
-        x = torch.randn(2, C, L)
-        y = blk(x)
-        amp.update({f"k{ks}.{k}": v.numpy() for k, v in sd.items()})
-        amp[f"k{ks}.x"] = x.numpy()
-        amp[f"k{ks}.y"] = y.numpy()
-    np.savez(os.path.join(GOLD, "ampblock1.npz"), **amp)
+    # 3. AMPBlock1 at a small width (reference class, own synthetic weights; uses the torch random stream,
+    #    so it is only reproducible in a full run) ---------------------------------------------
+    if want("amp"):
+        h = H(yaml.safe_load(open(f"{REF_ROOT}/checkpoints/config.yaml"))["bigvgan"])
+        h["use_cuda_kernel"] = False
+        amp = {}
+        for ks in (3, 7, 11):
+            C, L = 16, 160
+            blk = models.AMPBlock1(h, C, ks, (1, 3, 5), activation="snakebeta")
+            blk.remove_weight_norm()
+            blk.eval()
+            sd = {k: ((0.8 / (C * ks) ** 0.5) * torch.randn_like(v) if v.ndim == 3 and v.shape[-1] != 12 else
+                      (0.5 * torch.randn_like(v) if "act." in k else
+                       (0.1 * torch.randn_like(v) if k.endswith("bias") else v)))
+                  for k, v in blk.state_dict().items()}
+            blk.load_state_dict(sd)
+            x = torch.randn(2, C, L)
+            y = blk(x)
+            amp.update({f"k{ks}.{k}": v.numpy() for k, v in sd.items()})
+            amp[f"k{ks}.x"] = x.numpy()
+            amp[f"k{ks}.y"] = y.numpy()
+        np.savez(os.path.join(GOLD, "ampblock1.npz"), **amp)
 
     # 4. full generator + ECAPA with the synthetic weights --------------------------------
     sd_np = synth.make_state_dict(seed=1234)
-    g32 = ref_generator(models, sd_np)
+    g32 = g64 = None
+    if want("ecapa") or want("tiny") or want("cfg1") or want("logmel"):
+        g32 = ref_generator(models, sd_np)
+    if want("tiny") or want("cfg1"):
+        g64 = ref_generator(models, sd_np, torch.float64)
     # 4a. ECAPA on two prompts (one with relative lengths)
-    mel = synth.make_mel(seed=7, Tm=60, B=2)
-    emb = g32.speaker_encoder(torch.from_numpy(mel)).numpy()
-    lens = np.array([1.0, 0.6], dtype=np.float32)
-    emb_l = g32.speaker_encoder(torch.from_numpy(mel), torch.from_numpy(lens)).numpy()
-    np.savez(os.path.join(GOLD, "ecapa.npz"), mel=mel, emb=emb, lens=lens, emb_lens=emb_l)
+    if want("ecapa"):
+        mel = synth.make_mel(seed=7, Tm=60, B=2)
+        emb = g32.speaker_encoder(torch.from_numpy(mel)).numpy()
+        lens = np.array([1.0, 0.6], dtype=np.float32)
+        emb_l = g32.speaker_encoder(torch.from_numpy(mel), torch.from_numpy(lens)).numpy()
+        np.savez(os.path.join(GOLD, "ecapa.npz"), mel=mel, emb=emb, lens=lens, emb_lens=emb_l)
 
     # 4b. tiny full forward: B=2 (shared prompt, B'=1), T=6
-    x = synth.make_latents(0, 0, 2, 6)
-    mel1 = synth.make_mel(seed=7, Tm=60, B=1)
-    wav = g32(torch.from_numpy(x), torch.from_numpy(mel1))[0].numpy()
-    g64 = ref_generator(models, sd_np, torch.float64)
-    wav64 = g64(torch.from_numpy(x).double(), torch.from_numpy(mel1).double())[0].numpy()
-    emb1 = g32.speaker_encoder(torch.from_numpy(mel1)).numpy()
-    print("tiny: amp", np.abs(wav).max(), "std", wav.std(), "fp32-vs-fp64 maxabs", np.abs(wav - wav64).max())
-    np.savez(os.path.join(GOLD, "forward_tiny.npz"), x=x, mel=mel1, emb=emb1, wav=wav,
-             wav64=wav64.astype(np.float32))
+    if want("tiny"):
+        x = synth.make_latents(0, 0, 2, 6)
+        mel1 = synth.make_mel(seed=7, Tm=60, B=1)
+        wav = g32(torch.from_numpy(x), torch.from_numpy(mel1))[0].numpy()
+        wav64 = g64(torch.from_numpy(x).double(), torch.from_numpy(mel1).double())[0].numpy()
+        emb1 = g32.speaker_encoder(torch.from_numpy(mel1)).numpy()
+        print("tiny: amp", np.abs(wav).max(), "std", wav.std(), "fp32-vs-fp64 maxabs", np.abs(wav - wav64).max())
+        np.savez(os.path.join(GOLD, "forward_tiny.npz"), x=x, mel=mel1, emb=emb1, wav=wav,
+                 wav64=wav64.astype(np.float32))
 
-    # 4c. cfg1-sized forward: B=1, T=118 (~5 s), prompt Tm=400
-    x = synth.make_latents(1, 0, 1, 118)
-    mel4 = synth.make_mel(seed=7, Tm=400, B=1)
-    emb4 = g32.speaker_encoder(torch.from_numpy(mel4)).numpy()
-    wav = g32(torch.from_numpy(x), torch.from_numpy(mel4))[0].numpy()
-    wav64 = g64(torch.from_numpy(x).double(), torch.from_numpy(mel4).double())[0].numpy()
-    print("cfg1: amp", np.abs(wav).max(), "std", wav.std(), "fp32-vs-fp64 maxabs", np.abs(wav - wav64).max())
-    np.savez_compressed(os.path.join(GOLD, "forward_cfg1.npz"), emb=emb4, wav=wav.astype(np.float32),
-                        fp32_noise=np.float32(np.abs(wav - wav64).max()))
+    # 4c. the prompt fixture: tests/sample_prompt.wav -> 24 kHz audio and its log-mel [1,511,100] through the
+    #     reference's own front-end (BASELINE.json config 1: "ECAPA embedding from tests/sample_prompt.wav");
+    #     the audio is stored in fp32, exactly what the front-end saw.
+    audio24 = melp = None
+    if want("prompt") or want("cfg1"):
+        audio24, melp = prompt_mel()
+        print("prompt: audio", audio24.shape, "mel", melp.shape, "mean", melp.mean())
+    if want("prompt"):
+        np.savez_compressed(os.path.join(GOLD, "prompt.npz"), audio=audio24.astype(np.float32), mel=melp.astype(np.float32))
 
-    # 5. log-mel of the reference front-end (torchaudio) on the cfg1 waveform ---------------
-    try:
+    # 4d. config 1 of BASELINE.json: B=1, T=118 (~5 s), speaker embedding from the prompt wav's mel
+    if want("cfg1"):
+        x = synth.make_latents(1, 0, 1, 118)
+        mel4 = torch.from_numpy(melp)
+        emb4 = g32.speaker_encoder(mel4).numpy()
+        wav = g32(torch.from_numpy(x), mel4)[0].numpy()
+        wav64 = g64(torch.from_numpy(x).double(), mel4.double())[0].numpy()
+        print("cfg1: amp", np.abs(wav).max(), "std", wav.std(), "fp32-vs-fp64 maxabs", np.abs(wav - wav64).max())
+        np.savez_compressed(os.path.join(GOLD, "forward_cfg1.npz"), emb=emb4, wav=wav.astype(np.float32),
+                            fp32_noise=np.float32(np.abs(wav - wav64).max()))
+
+    # 5. log-mel of the reference front-end (torchaudio) on one second of a generated waveform -----------
+    if want("logmel"):
         sys.path.insert(0, REF_ROOT)
         from indextts.utils.feature_extractors import MelSpectrogramFeatures
+        x = synth.make_latents(1, 0, 1, 118)
+        wav = g32(torch.from_numpy(x), torch.from_numpy(synth.make_mel(seed=7, Tm=400, B=1)))[0].numpy()
         fe = MelSpectrogramFeatures()
         m = fe(torch.from_numpy(wav[:, 0, :24000])).numpy()
         np.savez_compressed(os.path.join(GOLD, "logmel.npz"), wav=wav[:, 0, :24000], mel=m)
-    except Exception as e:  # torchaudio missing pieces
-        print("logmel fixture skipped:", e)
 
 
 if __name__ == "__main__":

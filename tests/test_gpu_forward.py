@@ -14,7 +14,24 @@ pytestmark = pytest.mark.gpu
 
 FP32_MAXABS = 1e-3     # north_star gate
 FP32_MEL_L1 = 1e-3     # north_star gate
-BF16_SNR_DB = 25.0     # stated bound for the bf16 performance mode (measured margin in DESIGN.md)
+BF16_SNR_DB = 28.5     # stated bound for the bf16 performance mode: within 3 dB of what is measured (31.4-31.9 dB)
+
+
+def _oracle(x, emb, dtype=None):
+    """The CPU oracle (torch-operator restatement of the reference path, pinned to the reference's golden
+    waveforms in tests/test_oracle_golden.py), one call per batch item so ragged inputs need no padding."""
+    from b200vgan import synth
+    from oracle import bigvgan_torch_cpu as TC
+    import torch as _t
+    sd = TC.prepare_state_dict(synth.make_state_dict(1234, with_speaker_encoder=False))
+    return TC.bigvgan_forward_with_embedding(np.asarray(x), np.asarray(emb), sd)
+
+
+def _gate_fp32(tag, wav, ref):
+    err = float(np.abs(wav - ref).max())
+    mel = O.mel_l1(wav, ref)
+    print(tag, "fp32 max-abs", err, "mel-L1", mel)
+    assert err <= FP32_MAXABS and mel <= FP32_MEL_L1
 
 
 @pytest.fixture(scope="module")
@@ -58,7 +75,8 @@ def test_dropin_call_with_speaker_encoder(gen, golden_dir):
 
 
 def test_cfg1_fp32_matches_reference(gen, golden_dir):
-    """Config 1 of BASELINE.json: B=1, T=118 (~5 s)."""
+    """Config 1 of BASELINE.json: B=1, T=118 (~5 s); the speaker embedding is the reference ECAPA's output for the
+    mel of the reference's tests/sample_prompt.wav (tests/golden/prompt.npz, oracle/gen_golden.py)."""
     from b200vgan import synth
     g = np.load(os.path.join(golden_dir, "forward_cfg1.npz"))
     x = synth.make_latents(1, 0, 1, 118)
@@ -67,6 +85,20 @@ def test_cfg1_fp32_matches_reference(gen, golden_dir):
     mel = O.mel_l1(wav[:, 0], g["wav"][:, 0])
     print("cfg1 fp32 max-abs", err, "mel-L1", mel, "reference fp32-vs-fp64 noise", float(g["fp32_noise"]))
     assert err <= FP32_MAXABS and mel <= FP32_MEL_L1
+
+
+def test_cfg1_dropin_call_from_prompt_mel(gen, golden_dir):
+    """Config 1 through the reference call site: wav, _ = bigvgan(latent, mel_ref) with the prompt wav's mel
+    [1,511,100] -- native ECAPA kernels + decode against the unmodified reference's waveform."""
+    from b200vgan import synth
+    g = np.load(os.path.join(golden_dir, "forward_cfg1.npz"))
+    pr = np.load(os.path.join(golden_dir, "prompt.npz"))
+    gen.precision = "fp32"
+    x = torch.as_tensor(synth.make_latents(1, 0, 1, 118)).cuda()
+    emb = gen.speaker_embedding(torch.as_tensor(pr["mel"]).cuda()).cpu().numpy()
+    assert np.abs(emb - g["emb"]).max() <= 2e-4
+    wav, _ = gen(x, torch.as_tensor(pr["mel"]).cuda())
+    _gate_fp32("cfg1 drop-in", wav.cpu().numpy()[0, 0], g["wav"][0, 0])
 
 
 def test_cfg1_bf16_snr(gen, golden_dir):
@@ -152,6 +184,73 @@ def test_cfg2_bf16_vs_fp32_mode(gen):
     assert snr >= BF16_SNR_DB
 
 
+def test_cfg2_two_items_vs_oracle(gen):
+    """Config 2 (B=16 x 10 s, T=235): items 3 and 12 of the batch against the CPU oracle decoding them alone --
+    fp32 mode within the 1e-3 gates, bf16 mode within its SNR bound."""
+    from b200vgan import synth
+    x = synth.make_latents(2, 0, 16, 235)
+    emb = synth.make_speaker_embedding(B=1)
+    w32 = _run(gen, x, emb, "fp32")
+    w16 = _run(gen, x, emb, "bf16")
+    for i in (3, 12):
+        ref = _oracle(x[i:i + 1], emb)[0, 0]
+        _gate_fp32(f"cfg2 item {i}", w32[i, 0], ref)
+        snr = O.snr_db(ref, w16[i, 0])
+        print(f"cfg2 item {i} bf16 SNR dB", snr)
+        assert snr >= BF16_SNR_DB
+
+
+def test_cfg3_srt_segments_vs_oracle(gen):
+    """Config 3: "parity checked per segment against the oracle run one segment at a time".
+    Nine segments spanning the workload's length range (T = 24 ... 352) are taken out of the batched, ragged SRT
+    decode (fp32 and bf16 modes) and compared with the CPU oracle's stand-alone decode of the same latents."""
+    from b200vgan import sched, synth
+    frames = sched.srt_workload()
+    order = sorted(range(len(frames)), key=lambda i: (frames[i], i))
+    pick = sorted({order[int(round(q * (len(order) - 1)))] for q in np.linspace(0.0, 1.0, 9)})
+    assert frames[order[0]] == min(frames) and frames[order[-1]] == max(frames) and len(pick) >= 8
+    # decode them together with their neighbours in the length-sorted order, so the batches are really ragged
+    pos = {i: k for k, i in enumerate(order)}
+    idx = sorted({order[min(max(pos[i] + d, 0), len(order) - 1)] for i in pick for d in (-1, 0, 1)})
+    rng = np.random.default_rng(3)
+    lat = {i: rng.standard_normal((frames[i], 1024), dtype=np.float32) for i in idx}
+    lat_dev = [torch.from_numpy(lat[i]).cuda() if i in lat else None for i in range(len(frames))]
+    emb_np = synth.make_speaker_embedding(B=1)
+    emb = torch.from_numpy(emb_np).cuda()
+    out = {}
+    for precision in ("fp32", "bf16"):
+        gen.precision = precision
+        out[precision] = sched.decode_segments(gen, lat_dev, emb, indices=idx, max_batch_frames=2048, max_batch=8)
+    for i in pick:
+        ref = _oracle(lat[i][None], emb_np)[0, 0]
+        assert out["fp32"][i].shape[0] == frames[i] * 1024 == ref.shape[0]
+        _gate_fp32(f"cfg3 segment {i} (T={frames[i]})", out["fp32"][i].numpy(), ref)
+        snr = O.snr_db(ref, out["bf16"][i].numpy())
+        print(f"cfg3 segment {i} (T={frames[i]}) bf16 SNR dB", snr)
+        assert snr >= BF16_SNR_DB
+
+
+def test_cfg4_long_form_vs_oracle(gen):
+    """Config 4 (60 s, B=1, T=1407): the full waveform against the CPU oracle, with the first and the last 1.5 s
+    (where sequence-edge handling differs from tile-halo handling) asserted separately -- SURVEY 8d."""
+    from b200vgan import synth
+    T = 1407
+    x = synth.make_latents(4, 0, 1, T)
+    emb = synth.make_speaker_embedding(B=1)
+    ref = _oracle(x, emb)[0, 0]
+    w32 = _run(gen, x, emb, "fp32")[0, 0]
+    assert w32.shape == ref.shape == (T * 1024,)
+    edge = 36000                                    # 1.5 s at 24 kHz
+    _gate_fp32("cfg4 whole", w32, ref)
+    _gate_fp32("cfg4 first 1.5 s", w32[:edge], ref[:edge])
+    _gate_fp32("cfg4 last 1.5 s", w32[-edge:], ref[-edge:])
+    w16 = _run(gen, x, emb, "bf16")[0, 0]
+    for tag, sl in (("whole", slice(None)), ("first 1.5 s", slice(0, edge)), ("last 1.5 s", slice(-edge, None))):
+        snr = O.snr_db(ref[sl], w16[sl])
+        print("cfg4", tag, "bf16 SNR dB", snr)
+        assert snr >= BF16_SNR_DB
+
+
 def test_cfg3_srt_workload_batched_equals_single(gen):
     """Config 3 of BASELINE.json: 512 variable-length SRT segments (1-15 s), decoded in length-bucketed
     ragged batches (the per-GPU part of the sharded dubbing job).  Spot-checked segments must equal
@@ -176,6 +275,68 @@ def test_cfg3_srt_workload_batched_equals_single(gen):
     for i in few:
         ref = torch.clamp(32767 * out[i], -32767.0, 32767.0).type(torch.int16)
         assert pcm[i].dtype == torch.int16 and torch.equal(pcm[i], ref)
+
+
+def test_decode_sentences_replaces_infer_fast_chunk_loop(gen, golden_dir):
+    """sched.decode_sentences has the shape of the vocoder loop of IndexTTS.infer_fast (infer.py:439-463): a list of
+    [1,T_i,1024] sentence latents + the prompt mel -> int16 waveforms in order.  Every sentence must equal its
+    stand-alone decode through the reference call `bigvgan(latent, mel)` + the caller's clamp/cast, bit for bit
+    (the reference's time-concatenation of chunk_size=2 sentences does not have that property)."""
+    from b200vgan import sched
+    pr = np.load(os.path.join(golden_dir, "prompt.npz"))
+    mel = torch.as_tensor(pr["mel"]).cuda()
+    rng = np.random.default_rng(17)
+    lens = [31, 7, 118, 1, 64, 19, 64]
+    lat = [torch.from_numpy(rng.standard_normal((1, n, 1024), dtype=np.float32)).cuda() for n in lens]
+    for precision in ("fp32", "bf16"):
+        gen.precision = precision
+        before = gen.plans_created()
+        wavs = sched.decode_sentences(gen, lat, mel, max_batch_frames=160, max_batch=4)
+        assert len(wavs) == len(lens) and gen.plans_created() - before <= 4
+        for l, n, w in zip(lat, lens, wavs):
+            assert w.dtype == torch.int16 and tuple(w.shape) == (1, n * 1024) and not w.is_cuda
+            wav, _ = gen(l, mel)
+            ref = torch.clamp(32767 * wav.squeeze(1), -32767.0, 32767.0).type(torch.int16).cpu()
+            assert torch.equal(w, ref)
+
+
+def test_forward_ragged_equals_dense(gen):
+    """bvg_forward_ragged (back-to-back rows in, back-to-back samples out) == bvg_forward on the padded batch."""
+    from b200vgan import synth
+    lens = [9, 2, 5]
+    x = torch.as_tensor(synth.make_latents(7, 0, 3, 9)).cuda()
+    emb = torch.as_tensor(synth.make_speaker_embedding(B=1)).cuda()
+    rows = torch.cat([x[b, :n] for b, n in enumerate(lens)])
+    for precision in ("fp32", "bf16"):
+        gen.precision = precision
+        dense = gen.forward_with_embedding(x, emb, x_lens=lens)
+        flat = gen.forward_ragged(rows, lens, emb)
+        pcm = gen.forward_ragged(rows, lens, emb, pcm16=True)
+        off = 0
+        for b, n in enumerate(lens):
+            seg = dense[b, 0, : n * 1024]
+            assert torch.equal(flat[off:off + n * 1024], seg)
+            assert torch.equal(pcm[off:off + n * 1024], torch.clamp(32767 * seg, -32767.0, 32767.0).type(torch.int16))
+            off += n * 1024
+
+
+def test_forward_host_entry_point(gen):
+    """bvg_forward_host (pinned host latents in, host waveform out, one call) == the device entry point."""
+    import ctypes as C
+    from b200vgan import lib, synth
+    gen.precision = "bf16"
+    x = torch.as_tensor(synth.make_latents(8, 0, 2, 6))
+    emb = torch.as_tensor(synth.make_speaker_embedding(B=1)).cuda()
+    ref = gen.forward_with_embedding(x.cuda(), emb).cpu()
+    plan = gen._plan((6, 6), gen._mode())
+    ws = gen._ensure_workspace(int(gen._libh.bvg_plan_workspace_bytes(plan)), emb.device)
+    xh = x.pin_memory()
+    wav_h = torch.empty(2, 1, 6 * 1024).pin_memory()
+    x_dev, wav_dev = torch.empty_like(x, device="cuda"), torch.empty(2, 1, 6 * 1024, device="cuda")
+    lib.check(gen._libh.bvg_forward_host(gen._handle, plan, xh.data_ptr(), lib.F32, x_dev.data_ptr(), emb.data_ptr(), 1,
+                                         wav_h.data_ptr(), wav_dev.data_ptr(), ws.data_ptr(), ws.numel(),
+                                         torch.cuda.current_stream().cuda_stream))
+    assert torch.equal(wav_h, ref)
 
 
 def test_checkpoint_layout_gives_same_audio(gen, synth_sd):

@@ -100,7 +100,9 @@ def test_conv1d_cuda_core_fp32(case):
     np.testing.assert_allclose(y, ref - r - b[None, :, None], atol=2e-5, rtol=1e-5)
 
 
-CONVT_CASES = [(1, 32, 16, 37, 8, 4), (2, 16, 8, 5, 4, 4), (1, 48, 24, 130, 4, 2), (1, 64, 32, 1, 8, 4)]
+# the last three have p = (k-u)/2 > u: the final rows of a segment need q beyond len_in + 1 (q_extra = ceil(p/u))
+CONVT_CASES = [(1, 32, 16, 37, 8, 4), (2, 16, 8, 5, 4, 4), (1, 48, 24, 130, 4, 2), (1, 64, 32, 1, 8, 4),
+               (2, 16, 8, 131, 16, 4), (1, 24, 16, 3, 12, 2), (1, 8, 8, 128, 20, 4)]
 
 
 @pytest.mark.parametrize("case", CONVT_CASES)
@@ -135,7 +137,8 @@ def test_conv1d_tcgen05_bf16(case):
 
 
 @pytest.mark.parametrize("case", [(1, 64, 32, 100, 8, 4), (2, 192, 96, 50, 4, 4), (1, 48, 24, 300, 4, 2),
-                                  (1, 1536, 768, 40, 8, 4), (1, 96, 48, 129, 4, 2)])
+                                  (1, 1536, 768, 40, 8, 4), (1, 96, 48, 129, 4, 2),
+                                  (2, 64, 32, 127, 16, 4), (1, 48, 24, 256, 12, 2)])   # p > u (k = 4u, 6u)
 def test_conv_transpose1d_tcgen05_bf16(case):
     from tests import gpu_util as G
     B, Cin, Cout, T, k, u = case

@@ -105,3 +105,26 @@ def test_torch_cpu_port_matches_reference_golden(golden_dir):
     assert np.abs(y64 - g["wav64"]).max() < 2e-6      # the stored embedding is the reference's fp32 one
     yo = O.bigvgan_forward_with_embedding(g["x"], g["emb"], sd)
     assert np.abs(y64 - yo).max() < 1e-12            # torch port == numpy oracle on identical inputs
+
+
+def test_cfg1_prompt_fixture_pins_oracle(golden_dir, synth_sd):
+    """Config 1 of BASELINE.json: the speaker embedding comes from the reference's tests/sample_prompt.wav.
+    prompt.npz holds the 24 kHz audio and the reference front-end's log-mel [1,511,100]; forward_cfg1.npz the
+    reference's ECAPA embedding of that mel and its fp32 waveform.  Pins: oracle log-mel, oracle ECAPA and the
+    torch-CPU port of the generator."""
+    import torch
+    from oracle import bigvgan_torch_cpu as TC
+    from b200vgan import synth
+    pr = np.load(os.path.join(golden_dir, "prompt.npz"))
+    g = np.load(os.path.join(golden_dir, "forward_cfg1.npz"))
+    assert pr["mel"].shape == (1, 511, 100) and pr["audio"].shape == (1, 130560)
+    mel = O.log_mel(pr["audio"])                       # [1, 100, 511]
+    dm = np.abs(mel.transpose(0, 2, 1) - pr["mel"])     # the reference's STFT runs in fp32: quiet bins carry its noise
+    assert dm.max() <= 1e-3 and dm.mean() <= 1e-5
+    emb = O.ecapa_forward(pr["mel"], synth_sd)
+    assert np.abs(emb - g["emb"]).max() <= 2e-5 * max(1.0, np.abs(g["emb"]).max())
+    sd = synth.make_state_dict(1234, with_speaker_encoder=False)
+    x = synth.make_latents(1, 0, 1, 118)
+    y32 = TC.bigvgan_forward_with_embedding(x, g["emb"], TC.prepare_state_dict(sd))
+    assert np.abs(y32 - g["wav"]).max() <= 5e-5        # fp32 summation-order noise (reference's own: fp32_noise)
+    assert O.mel_l1(y32[:, 0], g["wav"][:, 0]) <= 1e-4
