@@ -287,6 +287,11 @@ cudaError_t launch_act_c8_mma(const ActArgs& a, cudaStream_t s) {
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(act1d_c8_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(act1d_c8_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    // keep the SMs at the maximum shared-memory carve-out, the one the persistent conv kernel needs: alternating
+    // act / conv launches then never wait for an L1 / shared-memory reconfiguration (BVG_CARVEOUT=0 to compare)
+    static const int carve = [] { const char* c = getenv("BVG_CARVEOUT"); return c ? atoi(c) : 1; }();
+    if (carve && e == cudaSuccess) e = cudaFuncSetAttribute(act1d_c8_mma_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (carve && e == cudaSuccess) e = cudaFuncSetAttribute(act1d_c8_mma_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
     attr_done = true;
   }

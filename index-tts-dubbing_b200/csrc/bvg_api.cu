@@ -300,9 +300,15 @@ int bvg_device_check(void) {
   cudaError_t e = cudaGetDeviceCount(&n);
   if (e != cudaSuccess || n == 0) return fail("no CUDA device: b200vgan has no CPU fallback (%s)", cudaGetErrorString(e));
   CK(cudaGetDevice(&dev));
-  cudaDeviceProp prop;
-  CK(cudaGetDeviceProperties(&prop, dev));
-  if (prop.major != 10) return fail("device %d is sm_%d%d; b200vgan is built for sm_100a only", dev, prop.major, prop.minor);
+  // cached per device: this runs at the top of every per-op entry point (cudaGetDeviceProperties costs milliseconds)
+  static int major_of_dev[64] = {0};
+  if (dev < 0 || dev >= 64) return fail("device index %d out of range", dev);
+  if (!major_of_dev[dev]) {
+    int major = 0;
+    CK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    major_of_dev[dev] = major ? major : -1;
+  }
+  if (major_of_dev[dev] != 10) return fail("device %d is sm_%dx; b200vgan is built for sm_100a only", dev, major_of_dev[dev]);
   return 0;
 }
 

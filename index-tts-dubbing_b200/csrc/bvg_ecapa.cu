@@ -6,13 +6,15 @@
 
 namespace {
 
-constexpr int TT = 64, TC = 32, CI = 8, MAXPAD = 8;   // econv tile: 64 time steps x 32 output channels, 8 input channels per step
+constexpr int BM = 64, BN = 32, BK = 16, MAXPAD = 8;   // econv tile: 64 output channels x 32 time steps, 16 reduction steps per stage
 
 struct EConv {
   const float* x; long long xb;     // input slice: element (b, c, t) at x[b*xb + c*T + t]
   const float* x2; long long x2b;   // optional addend with the same indexing (Res2Net: x_i + y_{i-1})
-  const float* w;                   // [Cout, Cin, K]
+  const float* w;                   // row co at w[co*wrs + wco ...]: Cin*K reduction weights, (ci, k) k fastest
+  long long wrs; int wco;
   const float* bias;                // [Cout] or nullptr
+  const float* bias_b;              // optional per-batch addend [B][Cout] (time-constant input channels folded into a bias)
   const float* scale; const float* shift;   // optional per-channel affine applied after the ReLU (folded BatchNorm)
   float* y; long long yb;
   int Cin, Cout, T, K, dil, relu, post;     // post: 0 none, 1 tanh, 2 sigmoid
@@ -25,61 +27,125 @@ __device__ __forceinline__ int reflect(int t, int T) {
   return min(max(t, 0), T - 1);
 }
 
-__global__ void __launch_bounds__(256) econv_kernel(const EConv a) {
-  __shared__ float xs[CI][TT + 2 * MAXPAD];
-  __shared__ float ws[TC][CI * 5 + 1];
-  const int t0 = blockIdx.x * TT, co0 = blockIdx.y * TC, b = blockIdx.z;
-  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  const int pad = a.dil * (a.K - 1) / 2, width = TT + 2 * pad, K = a.K;
+// Implicit-GEMM Conv1d on the FP32 pipe: D[co, t] = sum_r W[co, r] * X[r, t], r = (ci, k).  128 threads, each a 4 x 4
+// register tile; the next stage's operands are fetched into registers while the current one is multiplied (one barrier
+// per stage).  Grid: (time tiles, channel tiles, batch) -- 128 blocks for the 512-channel layers of a 511-frame prompt.
+__global__ void __launch_bounds__(128) econv_kernel(const EConv a) {
+  __shared__ __align__(16) float Ws[2][BK][BM + 4];
+  __shared__ __align__(16) float Xs[2][BK][BN + 4];
+  const int t0 = blockIdx.x * BN, co0 = blockIdx.y * BM, b = blockIdx.z;
+  const int tid = threadIdx.x, tx = tid & 7, ty = tid >> 3;
+  const int K = a.K, R = a.Cin * K, pad = a.dil * (K - 1) / 2;
   const float* xb = a.x + (size_t)b * a.xb;
   const float* x2b = a.x2 ? a.x2 + (size_t)b * a.x2b : nullptr;
-  float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-  for (int ci0 = 0; ci0 < a.Cin; ci0 += CI) {
-    for (int idx = tid; idx < CI * width; idx += 256) {
-      const int c = idx / width, j = idx - c * width;
-      float v = 0.f;
-      if (ci0 + c < a.Cin) {
-        const size_t off = (size_t)(ci0 + c) * a.T + reflect(t0 - pad + j, a.T);
-        v = xb[off];
-        if (x2b) v += x2b[off];
-      }
-      xs[c][j] = v;
-    }
-    for (int idx = tid; idx < TC * CI * K; idx += 256) {
-      const int co = idx / (CI * K), r = idx - co * (CI * K);
-      const int c = r / K, kk = r - c * K;
-      float v = 0.f;
-      if (co0 + co < a.Cout && ci0 + c < a.Cin) v = a.w[((size_t)(co0 + co) * a.Cin + ci0 + c) * K + kk];
-      ws[co][r] = v;
-    }
-    __syncthreads();
+  // operand fetch assignment: W -- row wr (of 64), 8 consecutive r from wh*8; X -- row xr (of 16), 4 consecutive t from xt
+  const int wr = tid >> 1, wh = tid & 1, xr = tid >> 3, xt = (tid & 7) * 4;
+  const bool wrow_ok = co0 + wr < a.Cout;
+  const float* wrow = a.w + (size_t)(co0 + wr) * a.wrs + a.wco;
+  const bool wvec = ((a.wrs | (long long)a.wco) & 3) == 0;   // 16-byte aligned weight rows
+  float wreg[8], xreg[4];
+  auto fetch = [&](int r0) {
+    const int rw = r0 + wh * 8;
+    if (wvec && wrow_ok && rw + 8 <= R) {
+      const float4 v0 = __ldg(reinterpret_cast<const float4*>(wrow + rw)), v1 = __ldg(reinterpret_cast<const float4*>(wrow + rw + 4));
+      wreg[0] = v0.x; wreg[1] = v0.y; wreg[2] = v0.z; wreg[3] = v0.w; wreg[4] = v1.x; wreg[5] = v1.y; wreg[6] = v1.z; wreg[7] = v1.w;
+    } else {
 #pragma unroll
-    for (int c = 0; c < CI; ++c)
-      for (int kk = 0; kk < K; ++kk) {
-        const float w0 = ws[ty * 2][c * K + kk], w1 = ws[ty * 2 + 1][c * K + kk];
-        const float* xp = &xs[c][tx * 4 + kk * a.dil];
+      for (int j = 0; j < 8; ++j) wreg[j] = (wrow_ok && rw + j < R) ? __ldg(wrow + rw + j) : 0.f;
+    }
+    const int r = r0 + xr;
+    if (r < R) {
+      const int ci = r / K, kk = r - ci * K;
+      const float* xc = xb + (size_t)ci * a.T;
+      const float* x2c = x2b ? x2b + (size_t)ci * a.T : nullptr;
+      const int tb = t0 + xt + kk * a.dil - pad;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { acc[0][i] = fmaf(w0, xp[i], acc[0][i]); acc[1][i] = fmaf(w1, xp[i], acc[1][i]); }
+      for (int j = 0; j < 4; ++j) {
+        const int t = reflect(tb + j, a.T);
+        float v = xc[t];
+        if (x2c) v += x2c[t];
+        xreg[j] = v;
       }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) xreg[j] = 0.f;
+    }
+  };
+  auto stash = [&](int buf) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) Ws[buf][wh * 8 + j][wr] = wreg[j];
+    *reinterpret_cast<float4*>(&Xs[buf][xr][xt]) = make_float4(xreg[0], xreg[1], xreg[2], xreg[3]);
+  };
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  fetch(0);
+  stash(0);
+  __syncthreads();
+  int buf = 0;
+  for (int r0 = 0; r0 < R; r0 += BK) {
+    const bool more = r0 + BK < R;
+    if (more) fetch(r0 + BK);
+#pragma unroll
+    for (int r = 0; r < BK; ++r) {
+      const float4 wv = *reinterpret_cast<const float4*>(&Ws[buf][r][ty * 4]);
+      const float4 xv = *reinterpret_cast<const float4*>(&Xs[buf][r][tx * 4]);
+      const float wa[4] = {wv.x, wv.y, wv.z, wv.w}, xa[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(wa[i], xa[j], acc[i][j]);
+    }
+    if (more) stash(buf ^ 1);
     __syncthreads();
+    buf ^= 1;
   }
 #pragma unroll
-  for (int j = 0; j < 2; ++j) {
-    const int co = co0 + ty * 2 + j;
+  for (int i = 0; i < 4; ++i) {
+    const int co = co0 + ty * 4 + i;
     if (co >= a.Cout) continue;
-    const float bv = a.bias ? a.bias[co] : 0.f;
+    float bv = a.bias ? a.bias[co] : 0.f;
+    if (a.bias_b) bv += a.bias_b[(size_t)b * a.Cout + co];
     const float sc = a.scale ? a.scale[co] : 1.f, sh = a.scale ? a.shift[co] : 0.f;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int t = t0 + tx * 4 + i;
+    for (int j = 0; j < 4; ++j) {
+      const int t = t0 + tx * 4 + j;
       if (t >= a.T) continue;
-      float v = acc[j][i] + bv;
+      float v = acc[i][j] + bv;
       if (a.relu) v = fmaxf(v, 0.f);
       v = v * sc + sh;
       if (a.post == 1) v = tanhf(v);
       else if (a.post == 2) v = 1.f / (1.f + expf(-v));
       a.y[(size_t)b * a.yb + (size_t)co * a.T + t] = v;
     }
+  }
+}
+
+// Length-1 "convolutions" (SE block, final fc) and time-constant input channels folded into a bias: one warp per output,
+// y[b, co] = post(relu?(sum_ci w[co*wrs + wco + ci] * x[b*xb + ci] + bias[co]))
+__global__ void __launch_bounds__(256) egemv_kernel(const float* __restrict__ x, long long xb, const float* __restrict__ w, long long wrs,
+                                                    int wco, const float* __restrict__ bias, float* __restrict__ y, int Cin, int Cout,
+                                                    int relu, int post) {
+  const int co = blockIdx.x * 8 + (threadIdx.x >> 5), b = blockIdx.y, lane = threadIdx.x & 31;
+  if (co >= Cout) return;
+  const float* wr = w + (size_t)co * wrs + wco;
+  const float* xr = x + (size_t)b * xb;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int ci = lane;
+  for (; ci + 96 < Cin; ci += 128) {
+    s0 = fmaf(__ldg(wr + ci), xr[ci], s0); s1 = fmaf(__ldg(wr + ci + 32), xr[ci + 32], s1);
+    s2 = fmaf(__ldg(wr + ci + 64), xr[ci + 64], s2); s3 = fmaf(__ldg(wr + ci + 96), xr[ci + 96], s3);
+  }
+  for (; ci < Cin; ci += 32) s0 = fmaf(__ldg(wr + ci), xr[ci], s0);
+  float v = (s0 + s1) + (s2 + s3);
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if (lane == 0) {
+    if (bias) v += bias[co];
+    if (relu) v = fmaxf(v, 0.f);
+    if (post == 2) v = 1.f / (1.f + expf(-v));
+    y[(size_t)b * Cout + co] = v;
   }
 }
 
@@ -174,17 +240,6 @@ __global__ void escale_res_kernel(const float* x, long long xb, const float* s, 
   }
 }
 
-// attn input = cat([x, mean.expand, std.expand], dim=1)   (ECAPA_TDNN.py:318-321); st = [mean(C), std(C)] per batch
-__global__ void ecat_kernel(const float* x, const float* st, float* y, int C, int T, int B) {
-  const size_t n = (size_t)B * 3 * C * T;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    const int t = (int)(i % T);
-    const int c = (int)((i / T) % (3 * C));
-    const int b = (int)(i / ((size_t)T * 3 * C));
-    y[i] = c < C ? x[((size_t)b * C + c) * T + t] : st[(size_t)b * 2 * C + (c - C)];
-  }
-}
-
 // mel [B, T, M] -> [B, M, T]   (ECAPA_TDNN.py:556 x.transpose(1, 2))
 __global__ void etranspose_kernel(const float* mel, float* y, int B, int T, int M) {
   const size_t n = (size_t)B * T * M;
@@ -231,16 +286,23 @@ struct Runner {
   int launches = 0;
   cudaError_t err = cudaSuccess;
   void check() { if (err == cudaSuccess) err = cudaGetLastError(); ++launches; }
-  void conv(const float* x, long long xb, const float* x2, long long x2b, const float* w, const float* bias, const float* scale,
-            const float* shift, float* y, long long yb, int Cin, int Cout, int T_, int K, int dil, int relu, int post) {
+  void conv(const float* x, long long xb, const float* x2, long long x2b, const float* w, long long wrs, int wco, const float* bias,
+            const float* bias_b, const float* scale, const float* shift, float* y, long long yb, int Cin, int Cout, int T_, int K,
+            int dil, int relu, int post) {
     if (K > 5 || dil * (K - 1) / 2 > MAXPAD) { err = cudaErrorInvalidValue; return; }
-    EConv a{x, xb, x2, x2b, w, bias, scale, shift, y, yb, Cin, Cout, T_, K, dil, relu, post};
-    dim3 grid((T_ + TT - 1) / TT, (Cout + TC - 1) / TC, B);
-    econv_kernel<<<grid, 256, 0, s>>>(a);
+    EConv a{x, xb, x2, x2b, w, wrs, wco, bias, bias_b, scale, shift, y, yb, Cin, Cout, T_, K, dil, relu, post};
+    dim3 grid((T_ + BN - 1) / BN, (Cout + BM - 1) / BM, B);
+    econv_kernel<<<grid, 128, 0, s>>>(a);
+    check();
+  }
+  // length-1 sequence: y[b, :] = post(relu?(W[:, wco : wco + Cin] x[b, :] + bias))
+  void gemv(const float* x, long long xb, const float* w, long long wrs, int wco, const float* bias, float* y, int Cin, int Cout,
+            int relu, int post) {
+    egemv_kernel<<<dim3((Cout + 7) / 8, B), 256, 0, s>>>(x, xb, w, wrs, wco, bias, y, Cin, Cout, relu, post);
     check();
   }
   void tdnn(const EcapaTdnn& L, const float* x, long long xb, const float* x2, long long x2b, float* y, long long yb, int post = 0) {
-    conv(x, xb, x2, x2b, L.w, L.b, L.scale, L.shift, y, yb, L.cin, L.cout, T, L.k, L.d, 1, post);
+    conv(x, xb, x2, x2b, L.w, (long long)L.cin * L.k, 0, L.b, nullptr, L.scale, L.shift, y, yb, L.cin, L.cout, T, L.k, L.d, 1, post);
   }
   int blocks(size_t n) const { size_t g = (n + 255) / 256; return (int)(g > 4096 ? 4096 : g); }
 };
@@ -305,7 +367,7 @@ Layout make_layout(const EcapaModel& m, int B, int T) {
   L.sev = take((size_t)B * C); L.seh = take((size_t)B * m.se); L.ses = take((size_t)B * C);
   L.mfa = take(BT * 3 * C);
   L.st = take((size_t)B * 6 * C);
-  L.cat = take(BT * 9 * C);
+  L.cat = take((size_t)B * m.att);   // time-constant part of the attention TDNN's input, as a per-batch bias
   L.a1 = take(BT * m.att);
   L.a2 = take(BT * 3 * C);
   L.pooled = take((size_t)B * 6 * C);
@@ -349,8 +411,8 @@ cudaError_t ecapa_forward(const EcapaModel& m, const float* mel, int B, int T, c
     // SEBlock (:228-242): masked mean over time -> conv1 -> ReLU -> conv2 -> sigmoid -> scale
     estats_kernel<<<dim3(C, B), 128, 0, s>>>(tc, CT, nullptr, rel_lens, ws + L.sev, C, C, T, 0);
     r.check();
-    r.conv(ws + L.sev, C, nullptr, 0, bl.se1.w, bl.se1.b, nullptr, nullptr, ws + L.seh, m.se, C, m.se, 1, 1, 1, 1, 0);
-    r.conv(ws + L.seh, m.se, nullptr, 0, bl.se2.w, bl.se2.b, nullptr, nullptr, ws + L.ses, C, m.se, C, 1, 1, 1, 0, 2);
+    r.gemv(ws + L.sev, C, bl.se1.w, C, 0, bl.se1.b, ws + L.seh, C, m.se, 1, 0);
+    r.gemv(ws + L.seh, m.se, bl.se2.w, m.se, 0, bl.se2.b, ws + L.ses, m.se, C, 0, 2);
     escale_res_kernel<<<r.blocks((size_t)B * C * T), 256, 0, s>>>(tc, CT, ws + L.ses, xin, xin_b, xout, C3T, C, T, B);
     r.check();
     xin = xout;
@@ -362,11 +424,13 @@ cudaError_t ecapa_forward(const EcapaModel& m, const float* mel, int B, int T, c
   const int C3 = 3 * C;
   estats_kernel<<<dim3(C3, B), 128, 0, s>>>(ws + L.mfa, C3T, nullptr, rel_lens, ws + L.st, 2 * C3, C3, T, 1);
   r.check();
-  ecat_kernel<<<r.blocks((size_t)B * 3 * C3 * T), 256, 0, s>>>(ws + L.mfa, ws + L.st, ws + L.cat, C3, T, B);
-  r.check();
-  r.tdnn(m.asp_tdnn, ws + L.cat, 3LL * C3 * T, nullptr, 0, ws + L.a1, (long long)m.att * T, 1 /* tanh */);
-  r.conv(ws + L.a1, (long long)m.att * T, nullptr, 0, m.asp_conv.w, m.asp_conv.b, nullptr, nullptr, ws + L.a2, C3T, m.att, C3, T, 1, 1,
-         0, 0);
+  // attn input = cat([x, mean.expand, std.expand], dim=1) (:318-321): the 2*C3 time-constant channels contribute a
+  // per-batch bias  W[:, C3:3*C3] [mean; std]  to the attention TDNN, so the concatenation is never materialised
+  r.gemv(ws + L.st, 2 * C3, m.asp_tdnn.w, 3LL * C3, C3, nullptr, ws + L.cat, 2 * C3, m.att, 0, 0);
+  r.conv(ws + L.mfa, C3T, nullptr, 0, m.asp_tdnn.w, 3LL * C3, 0, m.asp_tdnn.b, ws + L.cat, m.asp_tdnn.scale, m.asp_tdnn.shift, ws + L.a1,
+         (long long)m.att * T, C3, m.att, T, 1, 1, 1, 1 /* tanh */);
+  r.conv(ws + L.a1, (long long)m.att * T, nullptr, 0, m.asp_conv.w, m.att, 0, m.asp_conv.b, nullptr, nullptr, nullptr, ws + L.a2, C3T,
+         m.att, C3, T, 1, 1, 0, 0);
   esoftmax_kernel<<<dim3(C3, B), 128, 0, s>>>(ws + L.a2, rel_lens, C3, T);
   r.check();
   estats_kernel<<<dim3(C3, B), 128, 0, s>>>(ws + L.mfa, C3T, ws + L.a2, rel_lens, ws + L.pooled, 2 * C3, C3, T, 1);
@@ -374,7 +438,7 @@ cudaError_t ecapa_forward(const EcapaModel& m, const float* mel, int B, int T, c
   // asp_bn (:575) and the final 1x1 conv (:578), on a length-1 sequence
   eaffine_kernel<<<(B * 2 * C3 + 255) / 256, 256, 0, s>>>(ws + L.pooled, m.abn_scale, m.abn_shift, ws + L.pooled_bn, 2 * C3, B);
   r.check();
-  r.conv(ws + L.pooled_bn, 2 * C3, nullptr, 0, m.fc.w, m.fc.b, nullptr, nullptr, emb, m.lin, 2 * C3, m.lin, 1, 1, 1, 0, 0);
+  r.gemv(ws + L.pooled_bn, 2 * C3, m.fc.w, 2LL * C3, 0, m.fc.b, emb, 2 * C3, m.lin, 0, 0);
   if (launches) *launches = r.launches;
   return r.err;
 }

@@ -1,8 +1,9 @@
 // ECAPA-TDNN speaker encoder (mel [B',Tm,n_mels] -> embedding [B',1,512]) on CUDA cores, fp32.
 // Reference: indextts/BigVGAN/ECAPA_TDNN.py:429-581 (architecture defaults :470-481), nnet/CNN.py:305-545
 // (SpeechBrain Conv1d, "same" reflect padding), nnet/normalization.py:13-108 (BatchNorm1d, eval).
-// The encoder is ~1.8 latent frames' worth of FLOPs per prompt and its result is cached per prompt by
-// the caller, so it is written for exactness (fp32 FFMA, the reference's operation order), not speed.
+// fp32 FFMA throughout (7e-6 against the reference's embedding).  The reference call site bigvgan(latent, mel_ref)
+// runs it on every call, so it sits on the end-to-end path: register-tiled implicit-GEMM convolutions, warp-per-output
+// GEMVs for the length-1 layers, ~0.4 ms for a 511-frame prompt (round 1: 7 ms).
 #pragma once
 #include <cuda_runtime.h>
 
