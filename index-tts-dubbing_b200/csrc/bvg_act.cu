@@ -144,7 +144,8 @@ cudaError_t launch_act_c8(const ActArgs& a, int dtype, bool precise, cudaStream_
   // the batch (the two kernels round differently).  BVG_ACT_MMA=0 selects version 3; BVG_ACT_MMA_MINLEN a length threshold.
   static const int use_mma = [] { const char* e = getenv("BVG_ACT_MMA"); return e ? atoi(e) : 1; }();
   static const int mma_minlen = [] { const char* e = getenv("BVG_ACT_MMA_MINLEN"); return e ? atoi(e) : 1; }();
-  if (use_mma && dtype == 1 && !precise && a.max_len >= mma_minlen) return launch_act_c8_mma(a, s);
+  if (dtype == 2) return precise ? cudaErrorInvalidValue : launch_act_c8_mma(a, dtype, s);   // fp16 storage: tensor-core kernel only
+  if (use_mma && dtype == 1 && !precise && a.max_len >= mma_minlen) return launch_act_c8_mma(a, dtype, s);
   if (!use_v1) return launch_act_c8_v2(a, dtype, precise, rt, s);
   dim3 grid((a.max_len + TR - 1) / TR, a.C / 8, a.B), block(NTHREADS);
   if (dtype == 0) {

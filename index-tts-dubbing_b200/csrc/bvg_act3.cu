@@ -1,42 +1,45 @@
-// Activation1d (alias_free_torch/act.py:24-29) with both FIR filters on the tensor cores -- bf16 performance
-// mode, packed c8 layout.  Version 4 of the activation kernel.
+// Activation1d (alias_free_torch/act.py:24-29) with both FIR filters on the tensor cores -- the 16-bit performance
+// modes (bf16 or fp16 storage), packed c8 layout.  Version 5 of the activation kernel.
 //
 // Why: the register-streamed kernel (bvg_act2.cu) is bound by the FP32 pipe, and 25 of its 31 fp32
 // operations per element are FIR taps (tools/fma_bench.cu: 128 FMA lanes per SM per clock; packed f32x2
 // does not raise that).  Both FIRs are banded Toeplitz products over time, so they map onto
-// warp-level mma.sync.m16n8k16 (bf16 in, fp32 accumulate; tools/hmma_bench.cu: 0.49 MMAs per clock per
+// warp-level mma.sync.m16n8k16 (16-bit in, fp32 accumulate; tools/hmma_bench.cu: 0.49 MMAs per clock per
 // SM) and leave the CUDA cores the snake (3 fp32 + 1 MUFU per activated sample):
 //
 //   U^T[row, m]  = sum_i X^T[row, i] * G^T[i, m]      up-FIR   (A = input rows, B = constant taps)
 //   s'           = u - h cos(2 alpha u)               snake without its +h (added to y: sum of taps = 1)
 //   Y^T[row, t]  = sum_m S'^T[row, m] * F^T[m, t]     down-FIR (A = activated samples, B = constant taps)
 //
-// The 16 MMA rows are two independent "streams" of 8 channels (an 8-channel chunk x a 128-row time
-// tile each), the MMA columns are time.  The accumulator fragment of two consecutive up-FIR column
-// tiles IS the A fragment of one down-FIR K-step (same trick as P = softmax(S) in attention kernels),
-// so the 2x activated signal lives only in registers.  Operand movement: ldmatrix.trans turns the
-// staged [time][8 channels] rows into A fragments, stmatrix.trans writes the result rows back.
-// The up-FIR runs in bf16 (its A operand is the stored bf16 tensor; taps rounded to bf16, optionally split hi + lo,
-// BVG_ACT_MMA_UPLO=1); the down-FIR runs in fp16 (activated samples and taps rounded to 11 bits: finer than the 8 bits the
-// stored result keeps anyway, and fp16's range is ample for activation magnitudes).
+// The 16 MMA rows are two independent "streams" of 8 channels (an 8-channel chunk x a time tile each), the
+// MMA columns are time.  The accumulator fragment of two consecutive up-FIR column tiles IS the A fragment of
+// one down-FIR K-step (same trick as P = softmax(S) in attention kernels), so the 2x activated signal lives
+// only in registers.  Operand movement: ldmatrix.trans turns the staged [time][8 channels] rows into A
+// fragments, stmatrix.trans writes the result rows back.  The up-FIR runs in the storage type (its A operand
+// is the stored tensor; taps rounded to it, optionally split hi + lo, BVG_ACT_MMA_UPLO=1); the down-FIR runs in
+// fp16 (activated samples and taps rounded to 11 bits, saturating).
 //
-// Formulas:  u[m] = 2 sum_k f[k] x[(m+5-k)/2],  y[t] = sum_k f[k] s[2t+k-5], replicate
-// padding of the input (staged rows are clamped) and of the activated signal (the three outputs next to
-// each segment end are recomputed exactly, actcore::exact_clamped).
+// Formulas:  u[m] = 2 sum_k f[k] x[(m+5-k)/2],  y[t] = sum_k f[k] s[clamp(2t+k-5, 0, 2L-1)],
+// with replicate padding of the input (staged rows are clamped to the segment) AND of the activated 2x signal.
+// Version 5 handles the second padding inside the MMA pipeline: in the (at most two) tiles of a stream that
+// touch a segment end, the activated samples outside [0, 2L) are replaced by s[0] / s[2L-1] (one warp shuffle
+// each) before they enter the down-FIR -- the separate exact edge pass of version 4 (36 serial FIR evaluations
+// per edge tile, ~16 us per launch on short segments) is gone.  Also new: the tile length is chosen per launch
+// (balanced tiles, a whole number of waves when the problem is small), column tiles past a segment's end are
+// not computed, and the storage type is a template parameter (bf16 / fp16).
 #include <cstdlib>
+#include <type_traits>
 
 #include <cuda_fp16.h>
 
-#include "bvg_act_core.cuh"
 #include "bvg_common.cuh"
 
 namespace {
 
-constexpr int TW = 224;            // output rows per stream tile
-constexpr int XROWS = TW + 32;     // staged rows per stream: local time -8 .. TW+23
-constexpr int NJ = TW / 8;         // output column tiles per stream tile
+constexpr int TWMAX = 224;         // most output rows per stream tile
+constexpr int XROWS = TWMAX + 32;  // staged rows per stream: local time -8 .. TW+23
 constexpr int WPB = 8;             // warps per block
-constexpr int MINB = 3;            // resident blocks per SM the kernel is compiled for (<= 64 registers)
+constexpr int MINB = 3;            // resident blocks per SM the kernel is compiled for (<= 85 registers)
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
@@ -50,15 +53,18 @@ __device__ __forceinline__ void ldsm_x4_trans(uint32_t addr, uint32_t (&r)[4]) {
 __device__ __forceinline__ void stsm_x2_trans(uint32_t addr, uint32_t r0, uint32_t r1) {
   asm volatile("stmatrix.sync.aligned.m8n8.x2.trans.shared.b16 [%0], {%1,%2};" ::"r"(addr), "r"(r0), "r"(r1) : "memory");
 }
-__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-__device__ __forceinline__ void mma16816_f16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+// D = A B + C with separate C / D registers (a constant C needs no per-step moves)
+template <typename T>
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1, float c0, float c1,
+                                         float c2, float c3) {
+  if constexpr (std::is_same<T, __nv_bfloat16>::value)
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%11,%12,%13};"
+                 : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "f"(c0), "f"(c1), "f"(c2), "f"(c3));
+  else
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%11,%12,%13};"
+                 : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "f"(c0), "f"(c1), "f"(c2), "f"(c3));
 }
 // saturating (F2FP.SATFINITE, same cost): an activated sample beyond fp16's range (tiny beta) becomes +-65504 instead of
 // inf, which the symmetric down-FIR taps would turn into NaN across the output
@@ -71,33 +77,26 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);
 }
+template <typename T> __device__ __forceinline__ uint32_t pack_io(float lo, float hi) {
+  if constexpr (std::is_same<T, __nv_bfloat16>::value) return pack_bf16(lo, hi);
+  else return pack_f16(lo, hi);
+}
+template <typename T> __device__ __forceinline__ float round_io(float v) {
+  if constexpr (std::is_same<T, __nv_bfloat16>::value) return __bfloat162float(__float2bfloat16_rn(v));
+  else return __half2float(__float2half_rn(v));
+}
 __device__ __forceinline__ float tap(int k) {   // f[k], 0 outside 0..11 (kaiser_sinc_filter1d(0.25, 0.3, 12), symmetric)
   const float f[6] = {BVG_F0, BVG_F1, BVG_F2, BVG_F3, BVG_F4, BVG_F5};
   if (k < 0 || k > 11) return 0.f;
   return f[k < 6 ? k : 11 - k];
 }
-// constant B fragment {B[2t][g], B[2t+1][g]} / {B[2t+8][g], B[2t+9][g]} of a tap matrix B[k][n] = scale * f[idx(k, n)],
-// split into a bf16 "hi" part and the bf16 rounding residual "lo"
-template <typename F>
-__device__ __forceinline__ void tap_frag(F idx, float scale, int g, int t, uint32_t (&hi)[2], uint32_t (&lo)[2]) {
-#pragma unroll
-  for (int half = 0; half < 2; ++half) {
-    const int k0 = 2 * t + 8 * half;
-    const float v0 = scale * tap(idx(k0, g)), v1 = scale * tap(idx(k0 + 1, g));
-    const float h0 = __bfloat162float(__float2bfloat16_rn(v0)), h1 = __bfloat162float(__float2bfloat16_rn(v1));
-    hi[half] = pack_bf16(h0, h1);
-    lo[half] = pack_bf16(v0 - h0, v1 - h1);
-  }
-}
 
-struct Stream {
-  int chunk, tile0, L;        // 8-channel chunk, first output row, segment length (tile0 >= L: nothing to do)
-};
-
-template <bool UP_LO>   // UP_LO: add the bf16 rounding residual of the up-FIR taps (second MMA per column tile)
+// UP_LO: add the rounding residual of the up-FIR taps as a second MMA per column tile
+template <typename T, bool UP_LO>
 __global__ void __launch_bounds__(WPB * 32, MINB)
-act1d_c8_mma_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, const float* __restrict__ alpha,
+act1d_c8_mma_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __restrict__ alpha,
                     const float* __restrict__ inv_beta, const SegDesc* __restrict__ seg, int R, int ntiles, int nchunks,
+                    int tw /* output rows per tile (multiple of 8, <= TWMAX) */,
                     int GT /* consecutive time tiles a warp processes per stream: amortises the constant set-up */) {
   extern __shared__ uint4 smem4[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
@@ -109,21 +108,29 @@ act1d_c8_mma_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restri
   const int nitems = ngroups * nchunks;
   const int item0 = 2 * (blockIdx.x * WPB + warp);
   if (item0 >= nitems) return;   // warp-uniform; no block barrier is ever used
-  Stream st[2];
-  int first_tile[2];
+  int chunk[2], first_tile[2];
+  bool have[2];
 #pragma unroll
   for (int s = 0; s < 2; ++s) {
     const int it = item0 + s < nitems ? item0 + s : item0;
-    st[s].chunk = it / ngroups;
-    first_tile[s] = (it - st[s].chunk * ngroups) * GT * TW;
-    st[s].L = item0 + s < nitems ? L : 0;   // a missing second stream computes on a copy of the first and stores nothing
+    chunk[s] = it / ngroups;
+    first_tile[s] = (it - chunk[s] * ngroups) * GT * tw;
+    have[s] = item0 + s < nitems;   // a missing second stream computes on a copy of the first and stores nothing
   }
-  if (first_tile[0] >= L && (st[1].L == 0 || first_tile[1] >= L)) return;
+  if (first_tile[0] >= L && (!have[1] || first_tile[1] >= L)) return;
 
-  __nv_bfloat16* region = reinterpret_cast<__nv_bfloat16*>(smem4) + (size_t)warp * (2 * XROWS * 8);   // [stream][row][8 ch]
+  T* region = reinterpret_cast<T*>(smem4) + (size_t)warp * (2 * XROWS * 8);   // [stream][row][8 ch]
   // ---- constants: tap fragments and this thread's two channel rows (stream 0 / stream 1, channel g) ----
-  uint32_t gup_hi[2], gup_lo[2];                      // up-FIR:   B[k][n] = 2 f[n + 11 - 2k]
-  tap_frag([](int k, int n) { return n + 11 - 2 * k; }, 2.f, g, t, gup_hi, gup_lo);
+  // constant B fragment {B[2t][g], B[2t+1][g]} / {B[2t+8][g], B[2t+9][g]} of the up-FIR tap matrix B[k][n] = 2 f[n + 11 - 2k]
+  uint32_t gup_hi[2], gup_lo[2];
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const int k0 = 2 * t + 8 * half;
+    const float v0 = 2.f * tap(g + 11 - 2 * k0), v1 = 2.f * tap(g + 11 - 2 * (k0 + 1));
+    const float h0 = round_io<T>(v0), h1 = round_io<T>(v1);
+    gup_hi[half] = pack_io<T>(h0, h1);
+    gup_lo[half] = pack_io<T>(v0 - h0, v1 - h1);
+  }
   uint32_t fdn[3][2];                                 // down-FIR: B_d[k][n] = f[16 d + k - 2n + 5], d = -1, 0, +1, as fp16
 #pragma unroll
   for (int d = 0; d < 3; ++d)
@@ -135,8 +142,8 @@ act1d_c8_mma_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restri
   float a2[2], hh[2];
 #pragma unroll
   for (int s = 0; s < 2; ++s) {
-    a2[s] = 2.f * alpha[st[s].chunk * 8 + g];
-    hh[s] = 0.5f * inv_beta[st[s].chunk * 8 + g];
+    a2[s] = 2.f * alpha[chunk[s] * 8 + g];
+    hh[s] = 0.5f * inv_beta[chunk[s] * 8 + g];
   }
   const uint32_t reg_s = smem_addr(region);
   // ldmatrix row address of this lane: matrices 0..3 = (stream 0, rows +0..7), (stream 1, +0..7), (stream 0, +8..15), (stream 1, +8..15)
@@ -146,163 +153,224 @@ act1d_c8_mma_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restri
 
 #pragma unroll 1
   for (int gt = 0; gt < GT; ++gt) {
-  st[0].tile0 = first_tile[0] + gt * TW;
-  st[1].tile0 = first_tile[1] + gt * TW;
-  if (st[0].tile0 >= L && (st[1].L == 0 || st[1].tile0 >= L)) break;
-  // ---- stage the raw rows: region row r of stream s = x[clamp(tile0 - 8 + r, 0, L-1)] (replicate padding of the input) ----
-#pragma unroll
-  for (int s = 0; s < 2; ++s) {
-    const __nv_bfloat16* xs = x + ((size_t)st[s].chunk * R + sd.off) * 8;
-    __nv_bfloat16* rs = region + (size_t)s * XROWS * 8;
-    const int r0 = st[s].tile0 - 8;
-#pragma unroll
-    for (int i = 0; i < XROWS / 32; ++i) {
-      const int r = lane + 32 * i;
-      const int row = min(max(r0 + r, 0), L - 1);
-      cp_async16(rs + r * 8, xs + (size_t)row * 8);
-    }
-  }
-  if (gt + 1 < GT) {   // pull the next tile's rows towards L2 while this one is processed
+    int tile0[2], nrow[2];
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
-      const int row = st[s].tile0 + TW - 8 + lane * 8;   // one 128-byte line per lane covers 8 rows
-      if (row < L && lane * 8 < XROWS)
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(x + ((size_t)st[s].chunk * R + sd.off + row) * 8));
+      tile0[s] = first_tile[s] + gt * tw;
+      nrow[s] = have[s] ? min(L - tile0[s], tw) : 0;   // valid output rows of this tile (<= 0: none)
     }
-  }
-  cp_async_wait_all();
-  __syncwarp();
-
-  // ---- exact values of the outputs that see the replicate padding of the activated signal (computed from
-  //      the raw rows before the in-place output pass overwrites them): lane = (stream, end, channel pair) ----
-  float2 fix[3];
-  int fix_t[3] = {-1, -1, -1};
-  if (lane < 16) {
-    const int s = lane >> 3, end = (lane >> 2) & 1, cp = lane & 3;
-    if (st[s].L > 0) {
-      const int ch = st[s].chunk * 8 + 2 * cp;
-      const float fa0 = 2.f * alpha[ch], fa1 = 2.f * alpha[ch + 1], fh0 = 0.5f * inv_beta[ch], fh1 = 0.5f * inv_beta[ch + 1];
-      const __nv_bfloat16* col0 = region + (size_t)s * XROWS * 8 + 2 * cp;
+    const int nrmax = max(nrow[0], nrow[1]);
+    if (nrmax <= 0) break;
+    const int nJ = (nrmax + 7) >> 3;          // output column tiles to compute
+    const int need = 8 * nJ + 32;             // staged rows the main pass reads (local time -8 .. 8 nJ + 23)
+    // ---- stage the raw rows: region row r of stream s = x[clamp(tile0 - 8 + r, 0, L-1)] (replicate padding of the input) ----
 #pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        const int ts = end ? L - 3 + j : j;
-        if (ts >= 0 && ts < L && ts >= st[s].tile0 && ts < st[s].tile0 + TW && (end || ts < L - 3)) {
-          fix_t[j] = ts;
-          fix[j] = actcore::exact_clamped(col0, st[s].tile0 - 8, XROWS, ts, L, fa0, fa1, fh0, fh1);
-        }
+    for (int s = 0; s < 2; ++s) {
+      const T* xs = x + ((size_t)chunk[s] * R + sd.off) * 8;
+      T* rs = region + (size_t)s * XROWS * 8;
+      const int r0 = tile0[s] - 8;
+#pragma unroll
+      for (int i = 0; i < XROWS / 32; ++i) {
+        const int r = lane + 32 * i;
+        const int row = min(max(r0 + r, 0), L - 1);
+        if (r < need) cp_async16(rs + r * 8, xs + (size_t)row * 8);
       }
     }
-  }
-  __syncwarp();
-
-  // ---- main pass ----
-
-  // one up-FIR column tile j (activated samples 8j .. 8j+7 of both streams) -> packed bf16 pair per stream
-  auto up_tile = [&](int j, uint32_t& p0, uint32_t& p1) {
-    uint32_t xa[4];
-    ldsm_x4_trans(ld_base + (uint32_t)(4 * j + 5) * 16, xa);   // input rows 4j-3 .. 4j+12 (region row = local time + 8)
-    float c[4] = {0.f, 0.f, 0.f, 0.f};
-    mma16816(c, xa, gup_hi[0], gup_hi[1]);
-    if (UP_LO) mma16816(c, xa, gup_lo[0], gup_lo[1]);
-    const float s0 = fmaf(-hh[0], __cosf(a2[0] * c[0]), c[0]), s1 = fmaf(-hh[0], __cosf(a2[0] * c[1]), c[1]);
-    const float s2 = fmaf(-hh[1], __cosf(a2[1] * c[2]), c[2]), s3 = fmaf(-hh[1], __cosf(a2[1] * c[3]), c[3]);
-    p0 = pack_f16(s0, s1);   // fp16 keeps 11 bits of the activated sample (bf16: 8); its range is ample for activations
-    p1 = pack_f16(s2, s3);
-  };
-  uint32_t ap[4], ac[4], an[4];   // down-FIR A fragments of K-steps J-1, J, J+1 (16 activated samples each)
-  ap[0] = ap[1] = 0u;             // samples -16 .. -9 are never used (zero taps): skip their column tile
-  up_tile(-1, ap[2], ap[3]);
-  up_tile(0, ac[0], ac[1]);
-  up_tile(1, ac[2], ac[3]);
-  // one output column tile J (rows 8J .. 8J+7 of both streams); P / C / N = K-steps J-1, J, J+1 (N is produced here)
-  auto step = [&](int J, const uint32_t (&P)[4], const uint32_t (&C)[4], uint32_t (&N)[4], bool last) {
-    up_tile(2 * J + 2, N[0], N[1]);
-    if (!last) up_tile(2 * J + 3, N[2], N[3]);
-    else N[2] = N[3] = 0u;        // beyond the last sample any output of this tile needs
-    float c[4] = {hh[0], hh[0], hh[1], hh[1]};
-    mma16816_f16(c, P, fdn[0][0], fdn[0][1]);
-    mma16816_f16(c, C, fdn[1][0], fdn[1][1]);
-    mma16816_f16(c, N, fdn[2][0], fdn[2][1]);
-    // the raw rows these outputs overwrite were consumed by the column tiles above
-    stsm_x2_trans(st_base + (uint32_t)(8 * J) * 16, pack_bf16(c[0], c[1]), pack_bf16(c[2], c[3]));
-  };
-  // the J loop is unrolled by 3 with rotating fragment names; the last one to three column tiles follow separately
-  constexpr int NJ3 = ((NJ - 1) / 3) * 3;
-#pragma unroll 1
-  for (int J = 0; J < NJ3; J += 3) {
-    step(J, ap, ac, an, false);
-    step(J + 1, ac, an, ap, false);
-    step(J + 2, an, ap, ac, false);
-  }
-  if constexpr (NJ - NJ3 == 1) {
-    step(NJ - 1, ap, ac, an, true);
-  } else if constexpr (NJ - NJ3 == 2) {
-    step(NJ - 2, ap, ac, an, false);
-    step(NJ - 1, ac, an, ap, true);
-  } else {
-    step(NJ - 3, ap, ac, an, false);
-    step(NJ - 2, ac, an, ap, false);
-    step(NJ - 1, an, ap, ac, true);
-  }
-  __syncwarp();
-  // ---- patch the exact edge values in ----
-  if (lane < 16) {
-    const int s = lane >> 3, cp = lane & 3;
+    if (gt + 1 < GT) {   // pull the next tile's rows towards L2 while this one is processed
 #pragma unroll
-    for (int j = 0; j < 3; ++j)
-      if (fix_t[j] >= 0) actcore::stpair(region + ((size_t)s * XROWS + 8 + fix_t[j] - st[s].tile0) * 8 + 2 * cp, fix[j]);
-  }
-  __syncwarp();
-  // ---- copy the result rows out (16 bytes per lane, consecutive rows) ----
-#pragma unroll
-  for (int s = 0; s < 2; ++s) {
-    __nv_bfloat16* ys = y + ((size_t)st[s].chunk * R + sd.off + st[s].tile0) * 8;
-    const __nv_bfloat16* rs = region + ((size_t)s * XROWS + 8) * 8;
-    const int nrow = st[s].L - st[s].tile0;   // valid rows of this tile (<= 0: none)
-#pragma unroll
-    for (int i = 0; i < TW / 32; ++i) {
-      const int r = lane + 32 * i;
-      if (r < nrow) *reinterpret_cast<uint4*>(ys + (size_t)r * 8) = *reinterpret_cast<const uint4*>(rs + r * 8);
+      for (int s = 0; s < 2; ++s) {
+        const int row = tile0[s] + tw - 8 + lane * 8;   // one 128-byte line per lane covers 8 rows
+        if (row < L && lane * 8 < XROWS)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(x + ((size_t)chunk[s] * R + sd.off + row) * 8));
+      }
     }
+    cp_async_wait_all();
+    __syncwarp();
+
+    // ---- main pass ----
+    // does a stream's tile touch a segment end?  start: samples < 0 exist only in column tile -1 of the tile at time 0;
+    // end: a sample > hi = 2 (L - tile0) - 1 is read when the tile's last computed output row is within 3 rows of L
+    const bool edge = tile0[0] == 0 || tile0[1] == 0 || L - tile0[0] < 8 * nJ + 3 || L - tile0[1] < 8 * nJ + 3;
+
+    // one up-FIR column tile j: activated samples 8j .. 8j+7 (local) of both streams, v[0..1] stream 0, v[2..3] stream 1
+    auto up_vals = [&](int j, float (&v)[4]) {
+      uint32_t xa[4];
+      ldsm_x4_trans(ld_base + (uint32_t)(4 * j + 5) * 16, xa);   // input rows 4j-3 .. 4j+12 (region row = local time + 8)
+      float c[4];
+      mma16816<T>(c, xa, gup_hi[0], gup_hi[1], 0.f, 0.f, 0.f, 0.f);
+      if (UP_LO) mma16816<T>(c, xa, gup_lo[0], gup_lo[1], c[0], c[1], c[2], c[3]);
+      v[0] = fmaf(-hh[0], __cosf(a2[0] * c[0]), c[0]); v[1] = fmaf(-hh[0], __cosf(a2[0] * c[1]), c[1]);
+      v[2] = fmaf(-hh[1], __cosf(a2[1] * c[2]), c[2]); v[3] = fmaf(-hh[1], __cosf(a2[1] * c[3]), c[3]);
+    };
+    auto down = [&](int J, const uint32_t (&P)[4], const uint32_t (&C)[4], const uint32_t (&N)[4]) {
+      float c[4];
+      mma16816<__half>(c, P, fdn[0][0], fdn[0][1], hh[0], hh[0], hh[1], hh[1]);
+      mma16816<__half>(c, C, fdn[1][0], fdn[1][1], c[0], c[1], c[2], c[3]);
+      mma16816<__half>(c, N, fdn[2][0], fdn[2][1], c[0], c[1], c[2], c[3]);
+      // the raw rows these outputs overwrite were consumed by the column tiles above
+      stsm_x2_trans(st_base + (uint32_t)(8 * J) * 16, pack_io<T>(c[0], c[1]), pack_io<T>(c[2], c[3]));
+    };
+    uint32_t ap[4], ac[4], an[4];   // down-FIR A fragments of K-steps J-1, J, J+1 (16 activated samples each)
+    ap[0] = ap[1] = 0u;             // samples -16 .. -9 are never used (zero taps): skip their column tile
+
+    if (!edge) {
+      auto up_tile = [&](int j, uint32_t& p0, uint32_t& p1) {
+        float v[4];
+        up_vals(j, v);
+        p0 = pack_f16(v[0], v[1]);   // fp16 keeps 11 bits of the activated sample (bf16: 8); its range is ample for activations
+        p1 = pack_f16(v[2], v[3]);
+      };
+      up_tile(-1, ap[2], ap[3]);
+      up_tile(0, ac[0], ac[1]);
+      up_tile(1, ac[2], ac[3]);
+      // one output column tile J (rows 8J .. 8J+7 of both streams); P / C / N = K-steps J-1, J, J+1 (N is produced here)
+      auto step = [&](int J, const uint32_t (&P)[4], const uint32_t (&C)[4], uint32_t (&N)[4]) {
+        up_tile(2 * J + 2, N[0], N[1]);
+        up_tile(2 * J + 3, N[2], N[3]);
+        down(J, P, C, N);
+      };
+      // the J loop is unrolled by 3 with rotating fragment names; the remaining one or two column tiles follow
+      int J = 0;
+#pragma unroll 1
+      for (; J + 3 <= nJ; J += 3) {
+        step(J, ap, ac, an);
+        step(J + 1, ac, an, ap);
+        step(J + 2, an, ap, ac);
+      }
+      if (J < nJ) step(J, ap, ac, an);
+      if (J + 1 < nJ) step(J + 1, ac, an, ap);
+    } else {
+      // Tiles at a segment end: replicate padding of the ACTIVATED signal.  Column tiles are produced in increasing
+      // order, so the last in-segment sample s[hi] (column tile hi >> 3) is known before any sample beyond it.
+      int hi[2];
+      float e[2] = {0.f, 0.f};
+#pragma unroll
+      for (int s = 0; s < 2; ++s) hi[s] = 2 * (L - tile0[s]) - 1;
+      auto up_edge = [&](int j, float (&v)[4]) {
+        up_vals(j, v);
+        const int m0 = 8 * j + 2 * t;   // local index of v[0] / v[2]; v[1] / v[3] are m0 + 1
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          if (j == (hi[s] >> 3))   // warp-uniform
+            e[s] = __shfl_sync(0xffffffffu, (hi[s] & 1) ? v[2 * s + 1] : v[2 * s], (lane & ~3) | ((hi[s] & 7) >> 1));
+          if (m0 > hi[s]) v[2 * s] = e[s];
+          if (m0 + 1 > hi[s]) v[2 * s + 1] = e[s];
+        }
+      };
+      float v0[4], vm[4], v1[4];
+      up_edge(0, v0);
+      up_vals(-1, vm);
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        const float first = __shfl_sync(0xffffffffu, v0[2 * s], lane & ~3);   // s[0] of this channel
+        if (tile0[s] == 0) vm[2 * s] = vm[2 * s + 1] = first;
+        else if (hi[s] < 0) vm[2 * s] = vm[2 * s + 1] = 0.f;   // stream past its segment: nothing is stored
+      }
+      up_edge(1, v1);
+      ap[2] = pack_f16(vm[0], vm[1]); ap[3] = pack_f16(vm[2], vm[3]);
+      ac[0] = pack_f16(v0[0], v0[1]); ac[1] = pack_f16(v0[2], v0[3]);
+      ac[2] = pack_f16(v1[0], v1[1]); ac[3] = pack_f16(v1[2], v1[3]);
+#pragma unroll 1
+      for (int J = 0; J < nJ; ++J) {
+        float va[4], vb[4];
+        up_edge(2 * J + 2, va);
+        up_edge(2 * J + 3, vb);
+        an[0] = pack_f16(va[0], va[1]); an[1] = pack_f16(va[2], va[3]);
+        an[2] = pack_f16(vb[0], vb[1]); an[3] = pack_f16(vb[2], vb[3]);
+        down(J, ap, ac, an);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { ap[i] = ac[i]; ac[i] = an[i]; }
+      }
+    }
+    __syncwarp();
+    // ---- copy the result rows out (16 bytes per lane, consecutive rows) ----
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      T* ys = y + ((size_t)chunk[s] * R + sd.off + tile0[s]) * 8;
+      const T* rs = region + ((size_t)s * XROWS + 8) * 8;
+#pragma unroll
+      for (int i = 0; i < TWMAX / 32; ++i) {
+        const int r = lane + 32 * i;
+        if (r < nrow[s]) *reinterpret_cast<uint4*>(ys + (size_t)r * 8) = *reinterpret_cast<const uint4*>(rs + r * 8);
+      }
+    }
+    __syncwarp();   // the region is re-staged by the next tile
   }
-  __syncwarp();   // the region is re-staged by the next tile
+}
+
+// Tile length / tiles per warp for a launch.  Large launches (>= 3 waves of warps): balanced tiles of at most TWMAX
+// rows, two consecutive tiles per warp.  Small launches: the tile count that minimises  waves x (rows per tile +
+// fixed per-tile rows)  -- a short last wave costs a full one, and a launch that fills only part of the GPU gets
+// shorter tiles so that every SM has warps.
+struct ActTiling { int tw, ntiles, GT; };
+ActTiling choose_tiling(int max_len, int nchunks, int B, int num_sms) {
+  const long long slots = (long long)num_sms * MINB * WPB;   // resident warps
+  const int nt_min = (max_len + TWMAX - 1) / TWMAX;
+  auto tw_of = [&](int nt) { return ((max_len + nt - 1) / nt + 7) / 8 * 8; };
+  auto warps_of = [&](int nt) { return (long long)((nt * nchunks + 1) / 2) * B; };
+  if (warps_of(nt_min) >= 3 * slots) {
+    const int tw = tw_of(nt_min);
+    return ActTiling{tw, (max_len + tw - 1) / tw, 2};
   }
+  ActTiling best{tw_of(nt_min), nt_min, 1};
+  double best_cost = 1e30;
+  const int nt_max = max_len <= 32 ? 1 : (max_len + 31) / 32;
+  for (int nt = nt_min; nt <= nt_max && nt <= 8 * nt_min + 8; ++nt) {
+    const int tw = tw_of(nt);
+    if (tw > TWMAX) continue;
+    const int nt_eff = (max_len + tw - 1) / tw;
+    const long long w = warps_of(nt_eff);
+    const long long waves = (w + slots - 1) / slots;
+    // a partially filled single wave runs faster per warp (fewer warps share an SM): proportional above 1/3 full
+    double occ = waves == 1 ? (double)w / (double)slots : 1.0;
+    if (occ < 0.34) occ = 0.34;
+    const double cost = (double)waves * occ * (tw + 40.0);
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = ActTiling{tw, nt_eff, 1}; }
+  }
+  return best;
+}
+
+template <typename T>
+cudaError_t launch_t(const ActArgs& a, cudaStream_t s) {
+  static int sms_of_dev[64] = {0};   // per device: SM count and the function attributes
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+  const size_t smem = (size_t)WPB * 2 * XROWS * 16;
+  if (!sms_of_dev[dev]) {
+    int n = 0;
+    cudaError_t e = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(act1d_c8_mma_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(act1d_c8_mma_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    sms_of_dev[dev] = n > 0 ? n : 148;
+  }
+  const int nchunks = a.C / 8;
+  static const int force_tw = [] { const char* e = getenv("BVG_ACT_TW"); return e ? atoi(e) : 0; }();
+  ActTiling tl = choose_tiling(a.max_len, nchunks, a.B, sms_of_dev[dev]);
+  if (force_tw >= 8 && force_tw <= TWMAX) {
+    tl.tw = force_tw / 8 * 8; tl.ntiles = (a.max_len + tl.tw - 1) / tl.tw; tl.GT = tl.ntiles >= 2 ? 2 : 1;
+  }
+  const int nitems = ((tl.ntiles + tl.GT - 1) / tl.GT) * nchunks;
+  dim3 grid((nitems + 2 * WPB - 1) / (2 * WPB), 1, a.B), block(WPB * 32);
+  // BVG_ACT_MMA_UPLO=1 adds the rounding residual of the up-FIR taps (a second MMA per column tile): +0.4 dB of SNR
+  // on config 1 in the bf16 mode for ~4 % of the step time; off by default.
+  static const int up_lo = [] { const char* e = getenv("BVG_ACT_MMA_UPLO"); return e ? atoi(e) : 0; }();
+  if (!up_lo)
+    act1d_c8_mma_kernel<T, false><<<grid, block, smem, s>>>((const T*)a.x, (T*)a.y, a.alpha, a.inv_beta, a.seg, a.R, tl.ntiles, nchunks,
+                                                           tl.tw, tl.GT);
+  else
+    act1d_c8_mma_kernel<T, true><<<grid, block, smem, s>>>((const T*)a.x, (T*)a.y, a.alpha, a.inv_beta, a.seg, a.R, tl.ntiles, nchunks,
+                                                          tl.tw, tl.GT);
+  return cudaGetLastError();
 }
 
 }  // namespace
 
-// bf16 packed layout only; same contract as launch_act_c8 (bvg_act.cu).
-cudaError_t launch_act_c8_mma(const ActArgs& a, cudaStream_t s) {
+// 16-bit packed layout only (dtype 1 = bf16, 2 = fp16); same contract as launch_act_c8 (bvg_act.cu).
+cudaError_t launch_act_c8_mma(const ActArgs& a, int dtype, cudaStream_t s) {
   if (a.B <= 0 || a.max_len <= 0) return cudaSuccess;
-  const int ntiles = (a.max_len + TW - 1) / TW, nchunks = a.C / 8;
-  const int GT = ntiles >= 2 ? 2 : 1;
-  const int nitems = ((ntiles + GT - 1) / GT) * nchunks;
-  dim3 grid((nitems + 2 * WPB - 1) / (2 * WPB), 1, a.B), block(WPB * 32);
-  const size_t smem = (size_t)WPB * 2 * XROWS * 16;
-  static bool attr_done_dev[64] = {false};   // the attribute is per device
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
-  bool& attr_done = attr_done_dev[dev];
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(act1d_c8_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(act1d_c8_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    // keep the SMs at the maximum shared-memory carve-out, the one the persistent conv kernel needs: alternating
-    // act / conv launches then never wait for an L1 / shared-memory reconfiguration (BVG_CARVEOUT=0 to compare)
-    static const int carve = [] { const char* c = getenv("BVG_CARVEOUT"); return c ? atoi(c) : 1; }();
-    if (carve && e == cudaSuccess) e = cudaFuncSetAttribute(act1d_c8_mma_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    if (carve && e == cudaSuccess) e = cudaFuncSetAttribute(act1d_c8_mma_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    if (e != cudaSuccess) return e;
-    attr_done = true;
-  }
-  // BVG_ACT_MMA_UPLO=1 adds the bf16 rounding residual of the up-FIR taps (a second MMA per column tile): +0.4 dB of SNR
-  // (31.9 instead of 31.5 dB on config 1) for ~4 % of the step time; off by default.
-  static const int up_lo = [] { const char* e = getenv("BVG_ACT_MMA_UPLO"); return e ? atoi(e) : 0; }();
-  if (!up_lo)
-    act1d_c8_mma_kernel<false><<<grid, block, smem, s>>>((const __nv_bfloat16*)a.x, (__nv_bfloat16*)a.y, a.alpha, a.inv_beta, a.seg, a.R,
-                                                        ntiles, nchunks, GT);
-  else
-  act1d_c8_mma_kernel<true><<<grid, block, smem, s>>>((const __nv_bfloat16*)a.x, (__nv_bfloat16*)a.y, a.alpha, a.inv_beta, a.seg, a.R, ntiles,
-                                               nchunks, GT);
-  return cudaGetLastError();
+  if (dtype == 1) return launch_t<__nv_bfloat16>(a, s);
+  if (dtype == 2) return launch_t<__half>(a, s);
+  return cudaErrorInvalidValue;
 }

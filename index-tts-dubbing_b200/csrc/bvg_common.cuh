@@ -115,7 +115,7 @@ template <> __device__ __forceinline__ __half from_f32<__half>(float x) { return
 
 // host-side launchers (each returns cudaGetLastError())
 cudaError_t launch_act_c8(const ActArgs& a, int dtype, bool precise, cudaStream_t s);
-cudaError_t launch_act_c8_mma(const ActArgs& a, cudaStream_t s);
+cudaError_t launch_act_c8_mma(const ActArgs& a, int dtype, cudaStream_t s);   // dtype 1 = bf16, 2 = fp16
 cudaError_t launch_act_c8_v2(const ActArgs& a, int dtype, bool precise, int rt, cudaStream_t s);
 cudaError_t launch_act_nct(const void* x, void* y, const float* alpha, const float* inv_beta, int B, int C,
                            int T, int dtype, cudaStream_t s);

@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 i=0
 for cfg in "$@"; do
   out=gpurun_out/bench_${TAG}_$i.log
-  env $cfg BVG_PROF_DUMP=gpurun_out/dump_${TAG}_$i.txt timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $out 2>&1
+  env $cfg BVG_PROF_DUMP=gpurun_out/dump_${TAG}_$i.txt timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-srt > $out 2>&1
   echo "=== [$cfg] $(python -c "
 import json,sys
 try:
