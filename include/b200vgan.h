@@ -42,7 +42,9 @@ enum { BVG_F32 = 0, BVG_BF16 = 1, BVG_F16 = 2 };
 /* arithmetic mode of bvg_forward */
 enum {
   BVG_MODE_FP32 = 0, /* parity mode: fp32 storage, fp32 FFMA convolutions (CUDA cores)          */
-  BVG_MODE_BF16 = 1  /* performance mode: bf16 storage, tcgen05 bf16 MMA with fp32 accumulation  */
+  BVG_MODE_BF16 = 1, /* performance mode: bf16 storage, tcgen05 bf16 MMA with fp32 accumulation  */
+  BVG_MODE_F16 = 2   /* performance mode: fp16 storage (3 more mantissa bits, saturating stores), tcgen05 f16 MMA with
+                        fp32 accumulation -- what the reference runs under torch.amp.autocast(float16), infer.py:456,613 */
 };
 
 /* memory layout of the per-op test entry points */

@@ -127,7 +127,12 @@ class _AMPBlock1(nn.Module):
 
 
 class BigVGAN(nn.Module):
-    def __init__(self, h, use_cuda_kernel: bool = True, precision: str = "bf16"):
+    PRECISIONS = ("auto", "fp32", "fp16", "bf16")
+
+    def __init__(self, h, use_cuda_kernel: bool = True, precision: str = "auto"):
+        """`precision`: "fp32" (parity mode, the reference's default arithmetic), "fp16" / "bf16" (tensor-core modes
+        with 16-bit storage), or "auto" (default): what the reference module would compute in at this call site --
+        fp16 / bf16 under ``torch.amp.autocast`` with that dtype (infer.py:456, :613), fp32 otherwise."""
         super().__init__()
         self.h = h
         try:
@@ -294,7 +299,7 @@ class BigVGAN(nn.Module):
     def activation_kernel_name(self) -> str:
         """Which Activation1d kernel bvg_forward launches in the current precision mode (for bench reports)."""
         import os
-        if self.precision == "fp32":
+        if self.resolved_precision() == "fp32":
             return "act1d_c8_v3_kernel (Activation1d, register-streamed fp32)"
         if os.environ.get("BVG_ACT_MMA", "1") == "0":
             return "act1d_c8_v3_kernel (Activation1d, register-streamed, packed f32x2)"
@@ -303,8 +308,20 @@ class BigVGAN(nn.Module):
     def plans_created(self) -> int:
         return 0 if self._handle is None else int(self._libh.bvg_plans_created(self._handle))
 
+    def resolved_precision(self) -> str:
+        """The arithmetic the next forward will use ("auto" looks at the caller's autocast state)."""
+        p = self.precision
+        if p not in self.PRECISIONS:
+            raise _lib.BvgError(f"precision must be one of {self.PRECISIONS}, got {p!r}")
+        if p != "auto":
+            return p
+        if torch.is_autocast_enabled():
+            dt = torch.get_autocast_gpu_dtype()
+            return "fp16" if dt == torch.float16 else ("bf16" if dt == torch.bfloat16 else "fp32")
+        return "fp32"
+
     def _mode(self) -> int:
-        return _lib.MODE_FP32 if self.precision == "fp32" else _lib.MODE_BF16
+        return {"fp32": _lib.MODE_FP32, "bf16": _lib.MODE_BF16, "fp16": _lib.MODE_F16}[self.resolved_precision()]
 
     def num_launches(self, frames: Sequence[int]) -> int:
         return int(self._libh.bvg_plan_num_launches(self._plan(tuple(int(f) for f in frames), self._mode())))

@@ -40,6 +40,11 @@ constexpr int TWMAX = 224;         // most output rows per stream tile
 constexpr int XROWS = TWMAX + 32;  // staged rows per stream: local time -8 .. TW+23
 constexpr int WPB = 8;             // warps per block
 constexpr int MINB = 3;            // resident blocks per SM the kernel is compiled for (<= 85 registers)
+// Timing experiments (tools/act_exp.cu compiles this file with -DBVG_ACT_EXP=<bits>; results are numerically WRONG):
+// 1 = no cosine (MUFU), 2 = no down-FIR MMAs, 4 = no staging loads, 8 = no copy-out, 16 = no up-FIR MMA
+#ifndef BVG_ACT_EXP
+#define BVG_ACT_EXP 0
+#endif
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
@@ -173,7 +178,7 @@ act1d_c8_mma_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __r
       for (int i = 0; i < XROWS / 32; ++i) {
         const int r = lane + 32 * i;
         const int row = min(max(r0 + r, 0), L - 1);
-        if (r < need) cp_async16(rs + r * 8, xs + (size_t)row * 8);
+        if (r < need && !(BVG_ACT_EXP & 4)) cp_async16(rs + r * 8, xs + (size_t)row * 8);
       }
     }
     if (gt + 1 < GT) {   // pull the next tile's rows towards L2 while this one is processed
@@ -197,16 +202,27 @@ act1d_c8_mma_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __r
       uint32_t xa[4];
       ldsm_x4_trans(ld_base + (uint32_t)(4 * j + 5) * 16, xa);   // input rows 4j-3 .. 4j+12 (region row = local time + 8)
       float c[4];
-      mma16816<T>(c, xa, gup_hi[0], gup_hi[1], 0.f, 0.f, 0.f, 0.f);
+      if (BVG_ACT_EXP & 16) { c[0] = __uint_as_float(xa[0]); c[1] = __uint_as_float(xa[1]); c[2] = __uint_as_float(xa[2]); c[3] = __uint_as_float(xa[3]); }
+      else mma16816<T>(c, xa, gup_hi[0], gup_hi[1], 0.f, 0.f, 0.f, 0.f);
       if (UP_LO) mma16816<T>(c, xa, gup_lo[0], gup_lo[1], c[0], c[1], c[2], c[3]);
+      if (BVG_ACT_EXP & 1) {
+        v[0] = fmaf(-hh[0], a2[0] * c[0], c[0]); v[1] = fmaf(-hh[0], a2[0] * c[1], c[1]);
+        v[2] = fmaf(-hh[1], a2[1] * c[2], c[2]); v[3] = fmaf(-hh[1], a2[1] * c[3], c[3]);
+        return;
+      }
       v[0] = fmaf(-hh[0], __cosf(a2[0] * c[0]), c[0]); v[1] = fmaf(-hh[0], __cosf(a2[0] * c[1]), c[1]);
       v[2] = fmaf(-hh[1], __cosf(a2[1] * c[2]), c[2]); v[3] = fmaf(-hh[1], __cosf(a2[1] * c[3]), c[3]);
     };
     auto down = [&](int J, const uint32_t (&P)[4], const uint32_t (&C)[4], const uint32_t (&N)[4]) {
       float c[4];
+      if (BVG_ACT_EXP & 2) {
+        c[0] = __uint_as_float(P[2] ^ C[0] ^ N[0]); c[1] = __uint_as_float(P[3] ^ C[1] ^ N[1]);
+        c[2] = __uint_as_float(C[2] ^ N[2]); c[3] = __uint_as_float(C[3] ^ N[3]);
+      } else {
       mma16816<__half>(c, P, fdn[0][0], fdn[0][1], hh[0], hh[0], hh[1], hh[1]);
       mma16816<__half>(c, C, fdn[1][0], fdn[1][1], c[0], c[1], c[2], c[3]);
       mma16816<__half>(c, N, fdn[2][0], fdn[2][1], c[0], c[1], c[2], c[3]);
+      }
       // the raw rows these outputs overwrite were consumed by the column tiles above
       stsm_x2_trans(st_base + (uint32_t)(8 * J) * 16, pack_io<T>(c[0], c[1]), pack_io<T>(c[2], c[3]));
     };
@@ -291,7 +307,7 @@ act1d_c8_mma_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __r
 #pragma unroll
       for (int i = 0; i < TWMAX / 32; ++i) {
         const int r = lane + 32 * i;
-        if (r < nrow[s]) *reinterpret_cast<uint4*>(ys + (size_t)r * 8) = *reinterpret_cast<const uint4*>(rs + r * 8);
+        if (r < nrow[s] && !(BVG_ACT_EXP & 8)) *reinterpret_cast<uint4*>(ys + (size_t)r * 8) = *reinterpret_cast<const uint4*>(rs + r * 8);
       }
     }
     __syncwarp();   // the region is re-staged by the next tile

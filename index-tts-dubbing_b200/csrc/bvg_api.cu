@@ -50,6 +50,7 @@ struct ConvLayer {
   float* bias = nullptr;    // [Cout]
   float* w_tap = nullptr;   // [ntaps][Cin][N] fp32
   void* w_umma = nullptr;   // bf16 UMMA shared-memory images
+  void* w_umma16 = nullptr; // the same images in fp16 (BVG_MODE_F16)
   void setup() {
     if (!transposed) {
       ntaps = k; N = Cout; u = 1; p = 0; q_extra = 0;
@@ -211,7 +212,8 @@ ConvArgs make_conv_args(const ConvLayer& L, const bvg_plan* p, int gin, int gout
                         bool umma, const ActLayer* act = nullptr) {
   ConvArgs a{};
   a.x = x; a.y = y; a.res = res;
-  a.w = umma ? (const void*)L.w_umma : (const void*)L.w_tap;
+  a.dtype = p->dtype;
+  a.w = umma ? (const void*)(p->dtype == 2 ? L.w_umma16 : L.w_umma) : (const void*)L.w_tap;
   a.bias = bias; a.bias_bstride = bias_bstride;
   a.acc_img_scale = (float)p->h->nk;
   a.seg_in = p->seg_dev + (size_t)gin * p->B;
@@ -240,7 +242,7 @@ int run_conv(const ConvLayer& L, const bvg_plan* p, int gin, int gout, const voi
   // algorithmic work of this launch: 2 * Cin * taps * N MACs per input row (valid rows only)
   const double flops = 2.0 * L.Cin * L.ntaps * L.N * (double)p->sumlen[gin];
   const double bytes = ((double)L.Cin * p->sumlen[gin] + (double)L.Cout * p->sumlen[gout] * (res ? 2 : 1)) * p->esize;
-  if (p->mode == BVG_MODE_BF16 && L.w_umma) {
+  if (p->mode != BVG_MODE_FP32 && L.w_umma) {
     ConvArgs a = make_conv_args(L, p, gin, gout, x, y, res, bias, bias_bstride, scale, accumulate, true);
     if (conv_umma_supported(a)) {
       ProfScope ps(p->h, s, PROF_CONV_TC, flops, bytes);
@@ -453,7 +455,11 @@ static int finalize_conv(bvg_handle* h, ConvLayer& L, cudaStream_t s, bool want_
       if (!L.w_umma) {
         if (dev_alloc(h, &L.w_umma, bytes)) return 1;
       }
-      CK(launch_repack_umma(L.w_tap, L.w_umma, L.ntaps, L.Cin, L.N, (float)h->nk, s));
+      if (!L.w_umma16) {
+        if (dev_alloc(h, &L.w_umma16, bytes)) return 1;
+      }
+      CK(launch_repack_umma(L.w_tap, L.w_umma, 1, L.ntaps, L.Cin, L.N, (float)h->nk, s));
+      CK(launch_repack_umma(L.w_tap, L.w_umma16, 2, L.ntaps, L.Cin, L.N, (float)h->nk, s));
     }
   }
   return 0;
@@ -532,12 +538,12 @@ int bvg_speaker_embedding(bvg_handle* h, const float* mel, int32_t B, int32_t Tm
 
 int bvg_plan_create(bvg_handle* h, int32_t B, const int32_t* frames, int32_t mode, bvg_plan** out) {
   if (!h || !frames || !out || B < 1) return fail("bvg_plan_create: bad argument");
-  if (mode != BVG_MODE_FP32 && mode != BVG_MODE_BF16) return fail("bvg_plan_create: unknown mode %d", mode);
+  if (mode != BVG_MODE_FP32 && mode != BVG_MODE_BF16 && mode != BVG_MODE_F16) return fail("bvg_plan_create: unknown mode %d", mode);
   static uint64_t next_uid = 1;
   bvg_plan* p = new bvg_plan();
   p->uid = next_uid++;
   p->h = h; p->B = B; p->mode = mode;
-  p->dtype = mode == BVG_MODE_FP32 ? 0 : 1;
+  p->dtype = mode == BVG_MODE_FP32 ? 0 : (mode == BVG_MODE_BF16 ? 1 : 2);   // storage type of the packed tensors
   p->esize = p->dtype == 0 ? 4 : 2;
   p->frames.assign(frames, frames + B);
   const int ng = h->nups + 1;
@@ -824,7 +830,8 @@ int conv_op(bool transposed, const float* x, const float* w, const float* bias, 
   ConvLayer L;
   L.transposed = transposed; L.Cin = Cin; L.Cout = Cout; L.k = k; L.d = d; L.u = u; L.setup();
   if (!transposed && (k - 1) / 2 * d > BVG_GUARD - 6) return fail("conv op: halo exceeds guard rows");
-  const int dt = mode == BVG_MODE_FP32 ? 0 : 1;
+  if (mode != BVG_MODE_FP32 && mode != BVG_MODE_BF16 && mode != BVG_MODE_F16) return fail("conv op: unknown mode %d", mode);
+  const int dt = mode == BVG_MODE_FP32 ? 0 : (mode == BVG_MODE_BF16 ? 1 : 2);
   const size_t es = dt == 0 ? 4 : 2;
   const int Tout = T * u;
   OpTemps tmp;
@@ -851,6 +858,7 @@ int conv_op(bool transposed, const float* x, const float* w, const float* bias, 
   if (transposed) CK(launch_repack_convt(w, wt, Cin, Cout, k, u, s));
   else CK(launch_repack_conv(w, wt, Cout, Cin, k, s));
   ConvArgs a{};
+  a.dtype = dt;
   a.x = xc; a.y = yc; a.res = rc; a.w = wt; a.bias = bias; a.bias_bstride = 0; a.acc_img_scale = 1.f;
   a.seg_in = seg_dev; a.seg_out = seg_dev + B; a.Rx = Rin; a.Ry = Rout;
   a.Cin = Cin; a.Cout = Cout; a.ntaps = L.ntaps;
@@ -876,7 +884,7 @@ int conv_op(bool transposed, const float* x, const float* w, const float* bias, 
       a.x = ac; a.act_alpha = nullptr; a.act_inv_beta = nullptr;
     }
   }
-  if (mode == BVG_MODE_BF16) {
+  if (mode != BVG_MODE_FP32) {
     if (!a.act_alpha) a.msub = conv_umma_default_msub(a);
     std::vector<int> pf(B + 1, 0);
     for (int b = 0; b < B; ++b) pf[b + 1] = pf[b] + (T + L.q_extra + 128 * a.msub - 1) / (128 * a.msub);
@@ -888,7 +896,7 @@ int conv_op(bool transposed, const float* x, const float* w, const float* bias, 
     size_t bytes = umma_weight_image_bytes(L.ntaps, Cin, L.N);
     if (!bytes || !conv_umma_supported(a)) return fail("conv op: shape not supported by the tcgen05 kernel");
     if (tmp.alloc(&wu, bytes)) return 1;
-    CK(launch_repack_umma(wt, wu, L.ntaps, Cin, L.N, 1.f, s));
+    CK(launch_repack_umma(wt, wu, dt, L.ntaps, Cin, L.N, 1.f, s));
     a.w = wu;
     CK(launch_conv_umma(a, s));
   } else {
@@ -906,7 +914,8 @@ int bvg_activation1d_packed(const float* x, float* y, const float* log_alpha, co
   if (!x || !y || !log_alpha || !log_beta) return fail("bvg_activation1d_packed: null argument");
   if (C % 8 || B < 1 || T < 1) return fail("bvg_activation1d_packed: C must be a multiple of 8, B,T >= 1");
   cudaStream_t s = (cudaStream_t)stream;
-  const int dt = mode == BVG_MODE_FP32 ? 0 : 1;
+  if (mode != BVG_MODE_FP32 && mode != BVG_MODE_BF16 && mode != BVG_MODE_F16) return fail("bvg_activation1d_packed: unknown mode %d", mode);
+  const int dt = mode == BVG_MODE_FP32 ? 0 : (mode == BVG_MODE_BF16 ? 1 : 2);
   const size_t es = dt == 0 ? 4 : 2;
   OpTemps tmp;
   std::vector<SegDesc> seg(B);

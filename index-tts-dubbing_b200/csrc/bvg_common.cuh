@@ -47,6 +47,7 @@ struct ConvArgs {
   int max_q;            // max over segments of (len_in + q_extra)
   float out_scale;      // y = (acc + bias + res) * out_scale (+ y_old if accumulate)
   int accumulate;
+  int dtype;            // storage type of x / y / res: 0 = fp32, 1 = bf16, 2 = fp16 (tcgen05 kernel: 1 or 2)
   // tcgen05 kernel only: m-tile table (tile = 128*msub rows of q per segment)
   const int* tile_prefix;   // [B+1] prefix sum of tiles per segment (device)
   int total_mt;             // tile_prefix[B]
@@ -96,13 +97,32 @@ template <> struct Vec8<__nv_bfloat16> {
   }
 };
 
+template <> struct Vec8<__half> {
+  float v[8];
+  __device__ __forceinline__ void load(const __half* p) {
+    uint4 r = *reinterpret_cast<const uint4*>(p);
+    const __half2* h = reinterpret_cast<const __half2*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { float2 f = __half22float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+  }
+  __device__ __forceinline__ void store(__half* p) const {   // saturating: a value beyond fp16's range becomes +-65504, not inf
+    uint4 r;
+    uint32_t* h = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h[i]) : "f"(v[2 * i + 1]), "f"(v[2 * i]));
+    *reinterpret_cast<uint4*>(p) = r;
+  }
+};
+
 __device__ __forceinline__ float to_f32(float x) { return x; }
 __device__ __forceinline__ float to_f32(__nv_bfloat16 x) { return __bfloat162float(x); }
 __device__ __forceinline__ float to_f32(__half x) { return __half2float(x); }
 template <typename T> __device__ __forceinline__ T from_f32(float x);
 template <> __device__ __forceinline__ float from_f32<float>(float x) { return x; }
 template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float x) { return __float2bfloat16_rn(x); }
-template <> __device__ __forceinline__ __half from_f32<__half>(float x) { return __float2half_rn(x); }
+template <> __device__ __forceinline__ __half from_f32<__half>(float x) {
+  return __float2half_rn(fminf(fmaxf(x, -65504.f), 65504.f));
+}
 
 // kaiser_sinc_filter1d(0.25, 0.3, 12) -- reference alias_free_torch/filter.py:29-58; the taps are
 // symmetric, sum to 1 and are shared by UpSample1d and DownSample1d.

@@ -155,7 +155,9 @@ cudaError_t launch_conv_simt(const ConvArgs& a, int dtype, cudaStream_t s) {
   dim3 grid((a.max_q + TM - 1) / TM, (N + TN - 1) / TN, a.B), block(NT);
   if (dtype == 0)
     conv_simt_kernel<float><<<grid, block, 0, s>>>(a);
-  else
+  else if (dtype == 1)
     conv_simt_kernel<__nv_bfloat16><<<grid, block, 0, s>>>(a);
+  else
+    return cudaErrorInvalidValue;   // fp16 storage exists for the tcgen05 kernel only
   return cudaGetLastError();
 }

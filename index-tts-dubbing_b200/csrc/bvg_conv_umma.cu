@@ -192,16 +192,31 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   return d;
 }
 
+// F16: the tensors are stored in fp16 instead of bf16 (stores saturate at +-65504 instead of producing inf)
+template <bool F16>
 __device__ __forceinline__ void unpack_add(const uint4& p, float (&v)[8]) {
-  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&p);
+  if constexpr (F16) {
+    const __half2* h = reinterpret_cast<const __half2*>(&p);
 #pragma unroll
-  for (int j = 0; j < 4; ++j) { float2 f = __bfloat1622float2(h[j]); v[2 * j] += f.x; v[2 * j + 1] += f.y; }
+    for (int j = 0; j < 4; ++j) { float2 f = __half22float2(h[j]); v[2 * j] += f.x; v[2 * j + 1] += f.y; }
+  } else {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&p);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { float2 f = __bfloat1622float2(h[j]); v[2 * j] += f.x; v[2 * j + 1] += f.y; }
+  }
 }
+template <bool F16>
 __device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
   uint4 o;
-  __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+  if constexpr (F16) {
+    uint32_t* oh = reinterpret_cast<uint32_t*>(&o);
 #pragma unroll
-  for (int j = 0; j < 4; ++j) oh[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+    for (int j = 0; j < 4; ++j) asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(oh[j]) : "f"(v[2 * j + 1]), "f"(v[2 * j]));
+  } else {
+    __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) oh[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+  }
   return o;
 }
 
@@ -292,7 +307,7 @@ struct UmmaKernelArgs {
 
 struct TileRef { int nt, b, q0; };
 
-template <bool FUSE, int EPW = EPIW>
+template <bool FUSE, int EPW = EPIW, bool F16 = false>
 __global__ void __launch_bounds__(FUSE ? NTHREADS_FUSED : 64 + 32 * EPW, 1) conv_umma_kernel(const UmmaKernelArgs ka) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const ConvArgs& a = ka.c;
@@ -502,8 +517,8 @@ __global__ void __launch_bounds__(FUSE ? NTHREADS_FUSED : 64 + 32 * EPW, 1) conv
       auto run = [&](auto ms_tag, auto nk_tag) {
         constexpr int MS = decltype(ms_tag)::value;
         constexpr int NK = decltype(nk_tag)::value;   // K-steps per tap known at compile time (0 = runtime loop)
-        // instruction descriptor: D=f32, A=B=bf16, both K-major, N=BN, M=128
-        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(ka.BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        // instruction descriptor: D=f32, A=B=bf16 (format 1) or fp16 (format 0), both K-major, N=BN, M=128
+        const uint32_t idesc = (1u << 4) | (F16 ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)(ka.BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         const uint32_t lbo_a = (uint32_t)ka.astride * 16, lbo_b = (uint32_t)ka.BN * 16;
         // Descriptors differ only in the 14-bit start-address field (bits 0-13 of the low word).
         const uint64_t adesc0 = make_desc(0, lbo_a, 128), bdesc0 = make_desc(0, lbo_b, 128);
@@ -660,7 +675,7 @@ __global__ void __launch_bounds__(FUSE ? NTHREADS_FUSED : 64 + 32 * EPW, 1) conv
               v[2] = __uint_as_float(r[8 * u + 2]) + bv[2 * u].z; v[3] = __uint_as_float(r[8 * u + 3]) + bv[2 * u].w;
               v[4] = __uint_as_float(r[8 * u + 4]) + bv[2 * u + 1].x; v[5] = __uint_as_float(r[8 * u + 5]) + bv[2 * u + 1].y;
               v[6] = __uint_as_float(r[8 * u + 6]) + bv[2 * u + 1].z; v[7] = __uint_as_float(r[8 * u + 7]) + bv[2 * u + 1].w;
-              if (valid && nbase + 8 * u < N) *reinterpret_cast<uint4*>(yp + u * cs) = pack8(v);
+              if (valid && nbase + 8 * u < N) *reinterpret_cast<uint4*>(yp + u * cs) = pack8<F16>(v);
             }
           } else {
 #pragma unroll
@@ -670,7 +685,7 @@ __global__ void __launch_bounds__(FUSE ? NTHREADS_FUSED : 64 + 32 * EPW, 1) conv
               v[2] = (__uint_as_float(r[8 * u + 2]) + bv[2 * u].z) * osc; v[3] = (__uint_as_float(r[8 * u + 3]) + bv[2 * u].w) * osc;
               v[4] = (__uint_as_float(r[8 * u + 4]) + bv[2 * u + 1].x) * osc; v[5] = (__uint_as_float(r[8 * u + 5]) + bv[2 * u + 1].y) * osc;
               v[6] = (__uint_as_float(r[8 * u + 6]) + bv[2 * u + 1].z) * osc; v[7] = (__uint_as_float(r[8 * u + 7]) + bv[2 * u + 1].w) * osc;
-              if (valid && nbase + 8 * u < N) *reinterpret_cast<uint4*>(yp + u * cs) = pack8(v);
+              if (valid && nbase + 8 * u < N) *reinterpret_cast<uint4*>(yp + u * cs) = pack8<F16>(v);
             }
           }
         } else if (plain) {
@@ -709,11 +724,11 @@ __global__ void __launch_bounds__(FUSE ? NTHREADS_FUSED : 64 + 32 * EPW, 1) conv
             v[2] = __uint_as_float(r[8 * u + 2]) + bv[2 * u].z; v[3] = __uint_as_float(r[8 * u + 3]) + bv[2 * u].w;
             v[4] = __uint_as_float(r[8 * u + 4]) + bv[2 * u + 1].x; v[5] = __uint_as_float(r[8 * u + 5]) + bv[2 * u + 1].y;
             v[6] = __uint_as_float(r[8 * u + 6]) + bv[2 * u + 1].z; v[7] = __uint_as_float(r[8 * u + 7]) + bv[2 * u + 1].w;
-            if (rg && ok[u]) unpack_add(resv[u], v);
+            if (rg && ok[u]) unpack_add<F16>(resv[u], v);
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[j] *= a.out_scale;
-            if (accum_epi && ok[u]) unpack_add(oldv[u], v);
-            if (ok[u]) *reinterpret_cast<uint4*>(yg + base + u * cs) = pack8(v);
+            if (accum_epi && ok[u]) unpack_add<F16>(oldv[u], v);
+            if (ok[u]) *reinterpret_cast<uint4*>(yg + base + u * cs) = pack8<F16>(v);
           }
         } else {
           // transposed convolution: column n = (phase, channel), output row = q*u + phase - p.
@@ -746,7 +761,7 @@ __global__ void __launch_bounds__(FUSE ? NTHREADS_FUSED : 64 + 32 * EPW, 1) conv
             v[6] = __uint_as_float(r[8 * u + 6]) + b1[u].z; v[7] = __uint_as_float(r[8 * u + 7]) + b1[u].w;
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[j] *= a.out_scale;
-            if (ok[u]) *reinterpret_cast<uint4*>(yg + off[u]) = pack8(v);   // (no residual / accumulate for transposed layers)
+            if (ok[u]) *reinterpret_cast<uint4*>(yg + off[u]) = pack8<F16>(v);   // (no residual / accumulate for transposed layers)
           }
         }
       }
@@ -904,7 +919,8 @@ __global__ void __launch_bounds__(FUSE ? NTHREADS_FUSED : 64 + 32 * EPW, 1) conv
 }
 
 // fp32 [tap][Cin][N]  ->  bf16 images [ntile][kb][tap][chunk KC][n BN][8]
-__global__ void repack_umma_kernel(const float* __restrict__ wt, __nv_bfloat16* __restrict__ img, int ntaps, int Cin,
+template <typename T>
+__global__ void repack_umma_kernel(const float* __restrict__ wt, T* __restrict__ img, int ntaps, int Cin,
                                    int N, int KC, int NKB, int BN, int NT) {
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t total = (size_t)NT * NKB * ntaps * KC * BN * 8;
@@ -918,11 +934,12 @@ __global__ void repack_umma_kernel(const float* __restrict__ wt, __nv_bfloat16* 
   int nt = r / NKB;
   int ci = (kb * KC + c) * 8 + e, n = nt * BN + nn;
   float v = (ci < Cin && n < N) ? wt[((size_t)tap * Cin + ci) * N + n] : 0.f;
-  img[idx] = __float2bfloat16_rn(v);
+  img[idx] = from_f32<T>(v);
 }
 
 // identity images [kb][chunk KC][n BN][8] appended after the conv images of a square (Cin == N), single-n-tile layer
-__global__ void identity_umma_kernel(__nv_bfloat16* __restrict__ img, int N, int KC, int NKB, int BN, float value) {
+template <typename T>
+__global__ void identity_umma_kernel(T* __restrict__ img, int N, int KC, int NKB, int BN, float value) {
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t total = (size_t)NKB * KC * BN * 8;
   if (idx >= total) return;
@@ -932,7 +949,7 @@ __global__ void identity_umma_kernel(__nv_bfloat16* __restrict__ img, int N, int
   int c = r % KC;
   int kb = r / KC;
   int ci = (kb * KC + c) * 8 + e;
-  img[idx] = __float2bfloat16_rn((ci == nn && nn < N) ? value : 0.f);
+  img[idx] = from_f32<T>((ci == nn && nn < N) ? value : 0.f);
 }
 
 bool has_identity(const UmmaTiling& t, int Cin, int N) { return t.ok && t.NT == 1 && Cin == N; }
@@ -1073,19 +1090,25 @@ size_t umma_weight_image_bytes(int ntaps, int Cin, int N) {
   return (size_t)(t.NT * t.NKB * ntaps + (has_identity(t, Cin, N) ? 2 * t.NKB : 0)) * t.KC * t.BN * 16;
 }
 
-cudaError_t launch_repack_umma(const float* wp_tap_major, void* img, int ntaps, int Cin, int N, float acc_img_scale, cudaStream_t s) {
-  UmmaTiling t = make_tiling(ntaps, Cin, N);
-  if (!t.ok) return cudaErrorInvalidValue;
+template <typename T>
+static void repack_umma_t(const float* wp_tap_major, T* img, const UmmaTiling& t, int ntaps, int Cin, int N, float acc_img_scale,
+                          cudaStream_t s) {
   size_t total = (size_t)t.NT * t.NKB * ntaps * t.KC * t.BN * 8;
-  repack_umma_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(wp_tap_major, (__nv_bfloat16*)img, ntaps, Cin, N,
-                                                                    t.KC, t.NKB, t.BN, t.NT);
+  repack_umma_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(wp_tap_major, img, ntaps, Cin, N, t.KC, t.NKB, t.BN, t.NT);
   if (has_identity(t, Cin, N)) {
     const size_t itotal = (size_t)t.NKB * t.KC * t.BN * 8;
     // set 0: I (residual), set 1: acc_img_scale * I (old output of an accumulating layer; exact for small integers)
-    identity_umma_kernel<<<(unsigned)((itotal + 255) / 256), 256, 0, s>>>((__nv_bfloat16*)img + total, N, t.KC, t.NKB, t.BN, 1.f);
-    identity_umma_kernel<<<(unsigned)((itotal + 255) / 256), 256, 0, s>>>((__nv_bfloat16*)img + total + itotal, N, t.KC, t.NKB, t.BN,
-                                                                        acc_img_scale);
+    identity_umma_kernel<T><<<(unsigned)((itotal + 255) / 256), 256, 0, s>>>(img + total, N, t.KC, t.NKB, t.BN, 1.f);
+    identity_umma_kernel<T><<<(unsigned)((itotal + 255) / 256), 256, 0, s>>>(img + total + itotal, N, t.KC, t.NKB, t.BN, acc_img_scale);
   }
+}
+
+cudaError_t launch_repack_umma(const float* wp_tap_major, void* img, int dtype, int ntaps, int Cin, int N, float acc_img_scale,
+                               cudaStream_t s) {
+  UmmaTiling t = make_tiling(ntaps, Cin, N);
+  if (!t.ok || (dtype != 1 && dtype != 2)) return cudaErrorInvalidValue;
+  if (dtype == 1) repack_umma_t(wp_tap_major, (__nv_bfloat16*)img, t, ntaps, Cin, N, acc_img_scale, s);
+  else repack_umma_t(wp_tap_major, (__half*)img, t, ntaps, Cin, N, acc_img_scale, s);
   return cudaGetLastError();
 }
 
@@ -1112,7 +1135,7 @@ int conv_umma_fused_msub(const ConvArgs& a, bool force) {
   // activation is FP32-pipe bound and 10 activation warps per SM cannot outrun the stand-alone kernel.
   static const int enabled = env_int("BVG_FUSE_ACT", 0);
   static const int forced = env_int("BVG_CONV_MSUB", 0);
-  if (!(enabled || force) || !a.act_alpha) return 0;
+  if (!(enabled || force) || !a.act_alpha || a.dtype == 2) return 0;   // the fused activation warps are bf16 only
   const UmmaTiling t = make_tiling(a.ntaps, a.Cin, a.Cout);
   if (!t.ok || t.NT != 1 || a.u != 1) return 0;
   for (int msub = 4; msub >= 1; msub >>= 1) {
@@ -1127,7 +1150,9 @@ int conv_umma_fused_msub(const ConvArgs& a, bool force) {
 }
 
 bool conv_umma_supported(const ConvArgs& a) {
+  if (a.dtype != 1 && a.dtype != 2) return false;
   if (a.act_alpha) {
+    if (a.dtype != 1) return false;
     UmmaKernelArgs ka{};
     size_t smem;
     return a.tile_prefix != nullptr && configure_fused(a, a.msub, ka, smem);
@@ -1158,11 +1183,7 @@ cudaError_t launch_conv_umma(const ConvArgs& a, cudaStream_t s) {
     cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_umma_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX);
-    if (env_int("BVG_CARVEOUT", 1)) {
-      if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_umma_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-      if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_umma_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-      if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_umma_kernel<false, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    }
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_umma_kernel<false, EPIW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX);
     if (e != cudaSuccess) return e;
     sms_of_dev[dev] = n;
   }
@@ -1184,7 +1205,8 @@ cudaError_t launch_conv_umma(const ConvArgs& a, cudaStream_t s) {
   // blocks of a concurrent stream on the same SM (co-scheduling experiment, tools/two_stream.py)
   static const int epiw4 = env_int("BVG_CONV_EPIW", 8) == 4;
   dim3 grid(total_tiles < num_sms ? total_tiles : num_sms), block(fuse ? NTHREADS_FUSED : (epiw4 ? 64 + 32 * 4 : NTHREADS));
-  if (fuse) conv_umma_kernel<true><<<grid, block, smem, s>>>(ka);
+  if (a.dtype == 2 && !fuse) conv_umma_kernel<false, EPIW, true><<<grid, dim3(NTHREADS), smem, s>>>(ka);
+  else if (fuse) conv_umma_kernel<true><<<grid, block, smem, s>>>(ka);
   else if (epiw4) conv_umma_kernel<false, 4><<<grid, block, smem, s>>>(ka);
   else conv_umma_kernel<false><<<grid, block, smem, s>>>(ka);
   if (do_trace) {

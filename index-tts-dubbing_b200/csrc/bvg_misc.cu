@@ -185,8 +185,10 @@ cudaError_t launch_pack_latent(const void* x, int in_dtype, void* y, int out_dty
 #define PL(TI, TO) pack_latent_kernel<TI, TO><<<g, blk, 0, s>>>((const TI*)x, (TO*)y, seg, src_row, B, Tmax, C, R)
   if (out_dtype == 0) {
     if (in_dtype == 0) PL(float, float); else if (in_dtype == 1) PL(__nv_bfloat16, float); else PL(__half, float);
-  } else {
+  } else if (out_dtype == 1) {
     if (in_dtype == 0) PL(float, __nv_bfloat16); else if (in_dtype == 1) PL(__nv_bfloat16, __nv_bfloat16); else PL(__half, __nv_bfloat16);
+  } else {
+    if (in_dtype == 0) PL(float, __half); else if (in_dtype == 1) PL(__nv_bfloat16, __half); else PL(__half, __half);
   }
 #undef PL
   return cudaGetLastError();
@@ -197,7 +199,8 @@ cudaError_t launch_nct_to_c8(const float* x, void* y, int out_dtype, const SegDe
   size_t total = (size_t)B * C * T;
   if (!total) return cudaSuccess;
   if (out_dtype == 0) nct_to_c8_kernel<float><<<nblk(total, 256), 256, 0, s>>>(x, (float*)y, seg, B, C, T, R);
-  else nct_to_c8_kernel<__nv_bfloat16><<<nblk(total, 256), 256, 0, s>>>(x, (__nv_bfloat16*)y, seg, B, C, T, R);
+  else if (out_dtype == 1) nct_to_c8_kernel<__nv_bfloat16><<<nblk(total, 256), 256, 0, s>>>(x, (__nv_bfloat16*)y, seg, B, C, T, R);
+  else nct_to_c8_kernel<__half><<<nblk(total, 256), 256, 0, s>>>(x, (__half*)y, seg, B, C, T, R);
   return cudaGetLastError();
 }
 
@@ -206,7 +209,8 @@ cudaError_t launch_c8_to_nct(const void* x, int in_dtype, float* y, const SegDes
   size_t total = (size_t)B * C * T;
   if (!total) return cudaSuccess;
   if (in_dtype == 0) c8_to_nct_kernel<float><<<nblk(total, 256), 256, 0, s>>>((const float*)x, y, seg, B, C, T, R);
-  else c8_to_nct_kernel<__nv_bfloat16><<<nblk(total, 256), 256, 0, s>>>((const __nv_bfloat16*)x, y, seg, B, C, T, R);
+  else if (in_dtype == 1) c8_to_nct_kernel<__nv_bfloat16><<<nblk(total, 256), 256, 0, s>>>((const __nv_bfloat16*)x, y, seg, B, C, T, R);
+  else c8_to_nct_kernel<__half><<<nblk(total, 256), 256, 0, s>>>((const __half*)x, y, seg, B, C, T, R);
   return cudaGetLastError();
 }
 
@@ -223,7 +227,8 @@ cudaError_t launch_conv_post_tanh(const void* x, int dtype, const float* w, cons
   if (B <= 0 || Lmax <= 0) return cudaSuccess;
   dim3 g(nblk(Lmax, 256), B), blk(256);
   if (dtype == 0) conv_post_tanh_kernel<float><<<g, blk, 0, s>>>((const float*)x, w, bias, wav, pcm, seg, dst_row, hop, C, R, Lmax);
-  else conv_post_tanh_kernel<__nv_bfloat16><<<g, blk, 0, s>>>((const __nv_bfloat16*)x, w, bias, wav, pcm, seg, dst_row, hop, C, R, Lmax);
+  else if (dtype == 1) conv_post_tanh_kernel<__nv_bfloat16><<<g, blk, 0, s>>>((const __nv_bfloat16*)x, w, bias, wav, pcm, seg, dst_row, hop, C, R, Lmax);
+  else conv_post_tanh_kernel<__half><<<g, blk, 0, s>>>((const __half*)x, w, bias, wav, pcm, seg, dst_row, hop, C, R, Lmax);
   return cudaGetLastError();
 }
 

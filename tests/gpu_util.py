@@ -87,3 +87,7 @@ def conv_transpose1d(x, w, b, k, u, mode):
 
 def bf16_round(a):
     return torch.as_tensor(np.asarray(a, dtype=np.float32)).to(torch.bfloat16).float().numpy().astype(np.float64)
+
+
+def f16_round(a):
+    return torch.as_tensor(np.asarray(a, dtype=np.float32)).to(torch.float16).float().numpy().astype(np.float64)

@@ -15,6 +15,7 @@ pytestmark = pytest.mark.gpu
 FP32_MAXABS = 1e-3     # north_star gate
 FP32_MEL_L1 = 1e-3     # north_star gate
 BF16_SNR_DB = 28.5     # stated bound for the bf16 performance mode: within 3 dB of what is measured (31.4-31.9 dB)
+FP16_SNR_DB = 40.0     # stated bound for the fp16 performance mode (3 more mantissa bits in every stored tensor)
 
 
 def _oracle(x, emb, dtype=None):
@@ -99,6 +100,52 @@ def test_cfg1_dropin_call_from_prompt_mel(gen, golden_dir):
     assert np.abs(emb - g["emb"]).max() <= 2e-4
     wav, _ = gen(x, torch.as_tensor(pr["mel"]).cuda())
     _gate_fp32("cfg1 drop-in", wav.cpu().numpy()[0, 0], g["wav"][0, 0])
+
+
+def test_cfg1_fp16_snr(gen, golden_dir):
+    """fp16 storage mode (BVG_MODE_F16): what the reference deploys under torch.amp.autocast(float16), infer.py:456."""
+    from b200vgan import synth
+    g = np.load(os.path.join(golden_dir, "forward_cfg1.npz"))
+    x = synth.make_latents(1, 0, 1, 118)
+    wav = _run(gen, x, g["emb"], "fp16")
+    snr = O.snr_db(g["wav"], wav)
+    print("cfg1 fp16 SNR dB", snr, "max-abs", np.abs(wav - g["wav"]).max(), "mel-L1", O.mel_l1(wav[:, 0], g["wav"][:, 0]))
+    assert snr >= FP16_SNR_DB
+
+
+def test_fp16_mode_saturates_instead_of_overflowing(gen):
+    """Latents scaled x64 drive intermediate activations past fp16's range: stores saturate at +-65504 (no inf / NaN
+    reaches the waveform), and at x8 the mode still tracks the fp32 mode."""
+    from b200vgan import synth
+    emb = synth.make_speaker_embedding(B=1)
+    x = synth.make_latents(5, 0, 1, 40)
+    big = _run(gen, 64.0 * x, emb, "fp16")
+    assert np.isfinite(big).all() and np.abs(big).max() <= 1.0
+    ref8 = _run(gen, 8.0 * x, emb, "fp32")
+    got8 = _run(gen, 8.0 * x, emb, "fp16")
+    snr = O.snr_db(ref8, got8)
+    print("fp16 mode, latents x8: SNR dB vs fp32 mode", snr)
+    assert np.isfinite(got8).all() and snr >= 30.0
+
+
+def test_auto_precision_follows_autocast(gen, golden_dir):
+    """precision="auto" (the constructor default): fp32 like the reference module unless the caller is inside
+    torch.amp.autocast, then the autocast dtype (infer.py:456, :613)."""
+    from b200vgan import synth
+    g = np.load(os.path.join(golden_dir, "forward_cfg1.npz"))
+    x = torch.as_tensor(synth.make_latents(1, 0, 1, 118)).cuda()
+    emb = torch.as_tensor(g["emb"]).cuda()
+    gen.precision = "auto"
+    assert gen.resolved_precision() == "fp32"
+    w32 = gen.forward_with_embedding(x, emb).cpu().numpy()
+    with torch.amp.autocast("cuda", dtype=torch.float16):
+        assert gen.resolved_precision() == "fp16"
+        w16 = gen.forward_with_embedding(x, emb).cpu().numpy()
+    with torch.amp.autocast("cuda", dtype=torch.bfloat16):
+        assert gen.resolved_precision() == "bf16"
+    gen.precision = "fp32"
+    assert np.abs(w32 - g["wav"]).max() <= FP32_MAXABS
+    assert w16.dtype == np.float32 and O.snr_db(g["wav"], w16) >= FP16_SNR_DB
 
 
 def test_cfg1_bf16_snr(gen, golden_dir):

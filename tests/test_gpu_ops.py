@@ -49,19 +49,23 @@ def test_activation1d_half_types(dtype, tol):
 
 
 @pytest.mark.parametrize("shape", [(1, 8, 1), (2, 24, 7), (1, 8, 35), (2, 16, 131), (1, 48, 256), (3, 8, 1000),
-                                   (1, 24, 2 * 4096 + 301)])
-@pytest.mark.parametrize("mode", [0, 1])
+                                   (1, 24, 2 * 4096 + 301),
+                                   # tile-boundary cases of the tensor-core kernel: a tile ending 0..3 rows before the segment end
+                                   (1, 8, 2), (1, 8, 3), (1, 16, 8), (1, 8, 9), (2, 8, 223), (1, 16, 224), (1, 8, 225), (1, 8, 226),
+                                   (1, 8, 227), (1, 24, 449), (1, 8, 2 * 224 + 2), (16, 768, 96)])
+@pytest.mark.parametrize("mode", [0, 1, 2])
 def test_activation1d_packed_kernel(shape, mode):
-    """The hot-path kernel (packed c8 layout): interior fast path, sequence ends, short segments."""
+    """The hot-path kernel (packed c8 layout): interior fast path, sequence ends, short segments.  Mode 2 (fp16
+    storage) is the sharp check of the tensor-core kernel's segment-end handling: 3e-3 instead of bf16's 2e-2."""
     from tests import gpu_util as G
     rng = np.random.default_rng(sum(shape))
     x = (1.5 * rng.standard_normal(shape)).astype(np.float32)
     la = (0.5 * rng.standard_normal(shape[1])).astype(np.float32)
     lb = (0.5 * rng.standard_normal(shape[1])).astype(np.float32)
-    xin = x.astype(np.float64) if mode == 0 else G.bf16_round(x)
+    xin = x.astype(np.float64) if mode == 0 else (G.bf16_round(x) if mode == 1 else G.f16_round(x))
     ref = O.activation1d(xin, la.astype(np.float64), lb.astype(np.float64))
     y = G.activation1d_packed(x, la, lb, mode)
-    tol = 2e-5 if mode == 0 else 2e-2 * max(1.0, np.abs(ref).max())
+    tol = 2e-5 if mode == 0 else (2e-2 if mode == 1 else 3e-3) * max(1.0, np.abs(ref).max())
     assert np.abs(y - ref).max() <= tol, np.abs(y - ref).max()
 
 
@@ -134,6 +138,33 @@ def test_conv1d_tcgen05_bf16(case):
     y = G.conv1d(x, w, b, r, k, d, 1)
     scale = np.abs(ref).max()
     assert np.abs(y - ref).max() <= 8e-3 * scale, (np.abs(y - ref).max(), scale)
+
+
+@pytest.mark.parametrize("case", UMMA_CONV_CASES)
+def test_conv1d_tcgen05_fp16(case):
+    """fp16 storage mode (BVG_MODE_F16 = 2): kind::f16 MMAs on fp16 operands, saturating fp16 stores."""
+    from tests import gpu_util as G
+    B, Cin, Cout, T, k, d = case
+    x, w, b, r = _conv_inputs(B, Cin, Cout, T, k, 3)
+    ref = O.conv1d(G.f16_round(x), G.f16_round(w), b.astype(np.float64), dilation=d,
+                   padding=O.get_padding(k, d)) + G.f16_round(r)
+    y = G.conv1d(x, w, b, r, k, d, 2)
+    scale = np.abs(ref).max()
+    assert np.abs(y - ref).max() <= 1e-3 * scale, (np.abs(y - ref).max(), scale)
+
+
+@pytest.mark.parametrize("case", [(1, 64, 32, 100, 8, 4), (1, 48, 24, 300, 4, 2), (2, 64, 32, 127, 16, 4)])
+def test_conv_transpose1d_tcgen05_fp16(case):
+    from tests import gpu_util as G
+    B, Cin, Cout, T, k, u = case
+    rng = np.random.default_rng(4)
+    x = rng.standard_normal((B, Cin, T)).astype(np.float32)
+    w = (rng.standard_normal((Cin, Cout, k)) / np.sqrt(Cin * k / u)).astype(np.float32)
+    b = (0.1 * rng.standard_normal(Cout)).astype(np.float32)
+    ref = O.conv_transpose1d(G.f16_round(x), G.f16_round(w), b.astype(np.float64), u, (k - u) // 2)
+    y = G.conv_transpose1d(x, w, b, k, u, 2)
+    scale = np.abs(ref).max()
+    assert np.abs(y - ref).max() <= 1e-3 * scale, (np.abs(y - ref).max(), scale)
 
 
 @pytest.mark.parametrize("case", [(1, 64, 32, 100, 8, 4), (2, 192, 96, 50, 4, 4), (1, 48, 24, 300, 4, 2),
