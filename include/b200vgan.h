@@ -173,6 +173,18 @@ size_t bvg_ecapa_workspace_bytes(const bvg_handle* h, int32_t B, int32_t Tm);
 int bvg_speaker_embedding(bvg_handle* h, const float* mel, int32_t B, int32_t Tm, const float* rel_lens,
                           float* emb, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- prompt front-end -------------------------------------------------------------------------
+ * Replaces `cond_mel = MelSpectrogramFeatures()(audio)` (indextts/infer.py:513, utils/feature_extractors.py:24-50,
+ * padding="center"): torchaudio MelSpectrogram(n_fft 1024, periodic Hann, power 1, centre reflect padding, HTK mel
+ * scale, norm None) + safe_log = log(clip(x, 1e-7)) (utils/common.py:110-121), fp32.
+ *   audio  [B, n_samples] fp32 device, n_samples > 512
+ *   mel    fp32 device: [B, n_mels, frames] like the reference (transposed = 0) or [B, frames, n_mels], the layout
+ *          bvg_speaker_embedding / the module call take (transposed = 1); frames = bvg_mel_frames(n_samples, hop)
+ *   sample_rate 24000, hop 256, n_mels 100 (<= 128), f_min 0, f_max <= 0 meaning sample_rate / 2: the reference's values */
+int bvg_mel_frames(int32_t n_samples, int32_t hop);
+int bvg_log_mel(const float* audio, int32_t B, int32_t n_samples, int32_t sample_rate, int32_t hop, int32_t n_mels,
+                float f_min, float f_max, float* mel, int32_t transposed, void* stream);
+
 /* ---- per-op entry points (drop-in for the reference's native extension, and test hooks) ----
  *
  * bvg_activation1d: replaces anti_alias_activation_cuda.forward(x, up_f, down_f, alpha, beta)

@@ -2,11 +2,14 @@
 
 Importing this package never touches the oracle and never falls back to a CPU path."""
 from . import lib, sched, synth  # noqa: F401
-from .lib import BvgError, MODE_BF16, MODE_FP32  # noqa: F401
+from .lib import BvgError, MODE_BF16, MODE_F16, MODE_FP32  # noqa: F401
 
 
 def __getattr__(name):
     if name in ("BigVGAN", "Generator"):
         from .model import BigVGAN
         return BigVGAN
+    if name == "MelSpectrogramFeatures":
+        from .features import MelSpectrogramFeatures
+        return MelSpectrogramFeatures
     raise AttributeError(name)

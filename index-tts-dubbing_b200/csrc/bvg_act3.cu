@@ -156,6 +156,10 @@ act1d_c8_mma_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __r
   // stmatrix row address: matrices 0 / 1 = stream 0 / 1, row = output row within the column tile
   const uint32_t st_base = reg_s + (uint32_t)(((lane >> 3) & 1) * XROWS + 8 + (lane & 7)) * 16;
 
+  // everything above read launch constants only (segment table, snake parameters): from here on the previous kernel's
+  // output is read and its input buffer overwritten
+  pdl_trigger();
+  pdl_wait();
 #pragma unroll 1
   for (int gt = 0; gt < GT; ++gt) {
     int tile0[2], nrow[2];
@@ -373,12 +377,10 @@ cudaError_t launch_t(const ActArgs& a, cudaStream_t s) {
   // on config 1 in the bf16 mode for ~4 % of the step time; off by default.
   static const int up_lo = [] { const char* e = getenv("BVG_ACT_MMA_UPLO"); return e ? atoi(e) : 0; }();
   if (!up_lo)
-    act1d_c8_mma_kernel<T, false><<<grid, block, smem, s>>>((const T*)a.x, (T*)a.y, a.alpha, a.inv_beta, a.seg, a.R, tl.ntiles, nchunks,
-                                                           tl.tw, tl.GT);
-  else
-    act1d_c8_mma_kernel<T, true><<<grid, block, smem, s>>>((const T*)a.x, (T*)a.y, a.alpha, a.inv_beta, a.seg, a.R, tl.ntiles, nchunks,
-                                                          tl.tw, tl.GT);
-  return cudaGetLastError();
+    return launch_pdl(act1d_c8_mma_kernel<T, false>, grid, block, smem, s, (const T*)a.x, (T*)a.y, a.alpha, a.inv_beta, a.seg, a.R,
+                      tl.ntiles, nchunks, tl.tw, tl.GT);
+  return launch_pdl(act1d_c8_mma_kernel<T, true>, grid, block, smem, s, (const T*)a.x, (T*)a.y, a.alpha, a.inv_beta, a.seg, a.R,
+                    tl.ntiles, nchunks, tl.tw, tl.GT);
 }
 
 }  // namespace

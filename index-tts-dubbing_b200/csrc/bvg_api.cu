@@ -295,6 +295,7 @@ int run_act(const ActLayer& A, const bvg_plan* p, int g, const void* x, void* y,
 extern "C" {
 
 const char* bvg_last_error(void) { return g_err.c_str(); }
+int bvg_set_error(const char* msg) { return fail("%s", msg ? msg : "error"); }   // for the other translation units
 int bvg_version(void) { return 100; }
 
 int bvg_device_check(void) {

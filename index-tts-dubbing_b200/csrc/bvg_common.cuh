@@ -133,6 +133,26 @@ template <> __device__ __forceinline__ __half from_f32<__half>(float x) {
 #define BVG_F4 0.128572583f
 #define BVG_F5 0.443209797f
 
+// Programmatic dependent launch: a kernel launched through launch_pdl may start (block scheduling, prologue) while the
+// previous kernel of the stream drains; it must execute pdl_wait() before it touches anything an earlier kernel wrote
+// or still reads, and calls pdl_trigger() to let ITS successor do the same.  Both are no-ops in a plain launch.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+bool bvg_pdl_enabled();   // BVG_PDL (default 1)
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = bvg_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // host-side launchers (each returns cudaGetLastError())
 cudaError_t launch_act_c8(const ActArgs& a, int dtype, bool precise, cudaStream_t s);
 cudaError_t launch_act_c8_mma(const ActArgs& a, int dtype, cudaStream_t s);   // dtype 1 = bf16, 2 = fp16

@@ -366,6 +366,10 @@ __global__ void __launch_bounds__(FUSE ? NTHREADS_FUSED : 64 + 32 * EPW, 1) conv
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // programmatic dependent launch: the set-up above (barriers, TMEM, bias staging -- launch constants only) may run
+  // while the previous kernel drains; activations are read and outputs written only after it has completed
+  pdl_trigger();
+  pdl_wait();
 
   // low-overhead event trace (CTA 0 only): per-role ring in shared memory, flushed at kernel end
   unsigned long long* tr_smem = reinterpret_cast<unsigned long long*>(smem + (SMEM_MAX - 4 * 1024 * 8));
@@ -1205,10 +1209,12 @@ cudaError_t launch_conv_umma(const ConvArgs& a, cudaStream_t s) {
   // blocks of a concurrent stream on the same SM (co-scheduling experiment, tools/two_stream.py)
   static const int epiw4 = env_int("BVG_CONV_EPIW", 8) == 4;
   dim3 grid(total_tiles < num_sms ? total_tiles : num_sms), block(fuse ? NTHREADS_FUSED : (epiw4 ? 64 + 32 * 4 : NTHREADS));
-  if (a.dtype == 2 && !fuse) conv_umma_kernel<false, EPIW, true><<<grid, dim3(NTHREADS), smem, s>>>(ka);
-  else if (fuse) conv_umma_kernel<true><<<grid, block, smem, s>>>(ka);
-  else if (epiw4) conv_umma_kernel<false, 4><<<grid, block, smem, s>>>(ka);
-  else conv_umma_kernel<false><<<grid, block, smem, s>>>(ka);
+  cudaError_t le;
+  if (a.dtype == 2 && !fuse) le = launch_pdl(conv_umma_kernel<false, EPIW, true>, grid, dim3(NTHREADS), smem, s, ka);
+  else if (fuse) le = launch_pdl(conv_umma_kernel<true>, grid, block, smem, s, ka);
+  else if (epiw4) le = launch_pdl(conv_umma_kernel<false, 4>, grid, block, smem, s, ka);
+  else le = launch_pdl(conv_umma_kernel<false>, grid, block, smem, s, ka);
+  if (le != cudaSuccess) return le;
   if (do_trace) {
     cudaStreamSynchronize(s);
     static unsigned long long h[4 + 4 * 1024];

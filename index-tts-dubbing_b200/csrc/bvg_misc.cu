@@ -1,5 +1,7 @@
 // Small kernels around the convolution / activation hot ops: layout packing, weight repacking,
 // the speaker-conditioning projection folded into per-segment biases, and conv_post + tanh.
+#include <cstdlib>
+
 #include "bvg_common.cuh"
 #include "bvg_misc.cuh"
 
@@ -176,6 +178,11 @@ __global__ void zero_guards_all_kernel(const GuardJobs jobs, int B) {
 inline int nblk(size_t n, int t) { return (int)((n + t - 1) / t); }
 
 }  // namespace
+
+bool bvg_pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("BVG_PDL"); return e ? atoi(e) != 0 : true; }();
+  return on;
+}
 
 cudaError_t launch_pack_latent(const void* x, int in_dtype, void* y, int out_dtype, const SegDesc* seg,
                                const int* src_row, int B, int Tmax, int C, int R, cudaStream_t s) {
