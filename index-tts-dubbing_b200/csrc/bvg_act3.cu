@@ -51,6 +51,34 @@ __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(dst)), "l"(src));
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// bulk (TMA-engine) copies: one instruction moves a whole contiguous slab of rows
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "ACT_WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra ACT_WAIT_DONE;\n\t"
+      "bra ACT_WAIT_LOOP;\n\t"
+      "ACT_WAIT_DONE:\n\t"
+      "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void ldsm_x4_trans(uint32_t addr, uint32_t (&r)[4]) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
@@ -125,6 +153,14 @@ act1d_c8_mma_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __r
   if (first_tile[0] >= L && (!have[1] || first_tile[1] >= L)) return;
 
   T* region = reinterpret_cast<T*>(smem4) + (size_t)warp * (2 * XROWS * 8);   // [stream][row][8 ch]
+  // one mbarrier per warp (after the regions) for the bulk loads of interior tiles
+  const uint32_t bar = smem_addr(reinterpret_cast<uint8_t*>(smem4) + (size_t)WPB * 2 * XROWS * 16) + 8u * warp;
+  uint32_t bar_phase = 0;
+  if (lane == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
   // ---- constants: tap fragments and this thread's two channel rows (stream 0 / stream 1, channel g) ----
   // constant B fragment {B[2t][g], B[2t+1][g]} / {B[2t+8][g], B[2t+9][g]} of the up-FIR tap matrix B[k][n] = 2 f[n + 11 - 2k]
   uint32_t gup_hi[2], gup_lo[2];
@@ -172,17 +208,30 @@ act1d_c8_mma_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __r
     if (nrmax <= 0) break;
     const int nJ = (nrmax + 7) >> 3;          // output column tiles to compute
     const int need = 8 * nJ + 32;             // staged rows the main pass reads (local time -8 .. 8 nJ + 23)
-    // ---- stage the raw rows: region row r of stream s = x[clamp(tile0 - 8 + r, 0, L-1)] (replicate padding of the input) ----
+    // ---- stage the raw rows: region row r of stream s = x[clamp(tile0 - 8 + r, 0, L-1)] (replicate padding of the input).
+    //      Interior tiles (no clamping, both streams present): ONE bulk copy per stream, issued by lane 0 ----
+    const bool interior = have[1] && tile0[0] >= 8 && tile0[1] >= 8 && tile0[0] - 8 + need <= L && tile0[1] - 8 + need <= L;
+    if (lane == 0) bulk_wait_read();   // the previous tile's bulk store has finished reading the region
+    __syncwarp();
+    if (interior && !(BVG_ACT_EXP & 4)) {
+      if (lane == 0) {
+        mbar_expect_tx(bar, (uint32_t)(2 * need * 16));
 #pragma unroll
-    for (int s = 0; s < 2; ++s) {
-      const T* xs = x + ((size_t)chunk[s] * R + sd.off) * 8;
-      T* rs = region + (size_t)s * XROWS * 8;
-      const int r0 = tile0[s] - 8;
+        for (int s = 0; s < 2; ++s)
+          bulk_g2s(reg_s + (uint32_t)(s * XROWS * 16), x + ((size_t)chunk[s] * R + sd.off + tile0[s] - 8) * 8, (uint32_t)(need * 16), bar);
+      }
+    } else {
 #pragma unroll
-      for (int i = 0; i < XROWS / 32; ++i) {
-        const int r = lane + 32 * i;
-        const int row = min(max(r0 + r, 0), L - 1);
-        if (r < need && !(BVG_ACT_EXP & 4)) cp_async16(rs + r * 8, xs + (size_t)row * 8);
+      for (int s = 0; s < 2; ++s) {
+        const T* xs = x + ((size_t)chunk[s] * R + sd.off) * 8;
+        T* rs = region + (size_t)s * XROWS * 8;
+        const int r0 = tile0[s] - 8;
+#pragma unroll
+        for (int i = 0; i < XROWS / 32; ++i) {
+          const int r = lane + 32 * i;
+          const int row = min(max(r0 + r, 0), L - 1);
+          if (r < need && !(BVG_ACT_EXP & 4)) cp_async16(rs + r * 8, xs + (size_t)row * 8);
+        }
       }
     }
     if (gt + 1 < GT) {   // pull the next tile's rows towards L2 while this one is processed
@@ -193,8 +242,13 @@ act1d_c8_mma_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __r
           asm volatile("prefetch.global.L2 [%0];" ::"l"(x + ((size_t)chunk[s] * R + sd.off + row) * 8));
       }
     }
-    cp_async_wait_all();
-    __syncwarp();
+    if (interior && !(BVG_ACT_EXP & 4)) {
+      mbar_wait(bar, bar_phase);
+      bar_phase ^= 1u;
+    } else {
+      cp_async_wait_all();
+      __syncwarp();
+    }
 
     // ---- main pass ----
     // does a stream's tile touch a segment end?  start: samples < 0 exist only in column tile -1 of the tile at time 0;
@@ -302,20 +356,19 @@ act1d_c8_mma_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __r
         for (int i = 0; i < 4; ++i) { ap[i] = ac[i]; ac[i] = an[i]; }
       }
     }
+    // ---- copy the result rows out: one bulk store per stream (the rows are contiguous in the packed layout) ----
+    fence_async_smem();   // the stmatrix results (generic proxy) become visible to the bulk-copy engine
     __syncwarp();
-    // ---- copy the result rows out (16 bytes per lane, consecutive rows) ----
+    if (lane == 0 && !(BVG_ACT_EXP & 8)) {
 #pragma unroll
-    for (int s = 0; s < 2; ++s) {
-      T* ys = y + ((size_t)chunk[s] * R + sd.off + tile0[s]) * 8;
-      const T* rs = region + ((size_t)s * XROWS + 8) * 8;
-#pragma unroll
-      for (int i = 0; i < TWMAX / 32; ++i) {
-        const int r = lane + 32 * i;
-        if (r < nrow[s] && !(BVG_ACT_EXP & 8)) *reinterpret_cast<uint4*>(ys + (size_t)r * 8) = *reinterpret_cast<const uint4*>(rs + r * 8);
-      }
+      for (int s = 0; s < 2; ++s)
+        if (nrow[s] > 0)
+          bulk_s2g(y + ((size_t)chunk[s] * R + sd.off + tile0[s]) * 8, reg_s + (uint32_t)((s * XROWS + 8) * 16), (uint32_t)(nrow[s] * 16));
+      bulk_commit();
     }
-    __syncwarp();   // the region is re-staged by the next tile
+    __syncwarp();   // the region is re-staged by the next tile (after bulk_wait_read)
   }
+  if (lane == 0) bulk_wait_read();   // shared memory must stay valid until the last bulk store has read it
 }
 
 // Tile length / tiles per warp for a launch.  Large launches (>= 3 waves of warps): balanced tiles of at most TWMAX
@@ -356,7 +409,7 @@ cudaError_t launch_t(const ActArgs& a, cudaStream_t s) {
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
-  const size_t smem = (size_t)WPB * 2 * XROWS * 16;
+  const size_t smem = (size_t)WPB * 2 * XROWS * 16 + 8 * WPB;   // row regions + one mbarrier per warp
   if (!sms_of_dev[dev]) {
     int n = 0;
     cudaError_t e = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
