@@ -185,6 +185,19 @@ int bvg_mel_frames(int32_t n_samples, int32_t hop);
 int bvg_log_mel(const float* audio, int32_t B, int32_t n_samples, int32_t sample_rate, int32_t hop, int32_t n_mels,
                 float f_min, float f_max, float* mel, int32_t transposed, void* stream);
 
+/* ---- dubbing timeline ---------------------------------------------------------------------------
+ * The sum / normalise part of AudioProcessor._time_synchronized_merge (srt_dubbing/src/audio_processor.py:176-232):
+ *   out[t] = sum over the segments i covering t, in ascending seg_rank[i], of flat[seg_src[i] + t - seg_dst[i]]   (fp32)
+ *   normalize != 0:  out /= max|out|  when that peak exceeds max_amplitude (AUDIO.MAX_AMPLITUDE = 1.0)
+ * flat: the decoded segments back to back (device fp32); seg_src / seg_dst (int64) / seg_n (int32): device arrays of
+ * nseg entries, seg_dst ascending, seg_rank (int32) = each segment's position in the reference's adding order
+ * (start-time order; it differs from the seg_dst order when the overlap rule moved a segment); max_n = max seg_n; at most 16 segments may
+ * cover one sample; out [total] device fp32; peak_scratch: 4 bytes of device memory (needed when normalize != 0).
+ * The placement arithmetic (sorting, overlap rule, array growth) is host logic: b200vgan/timeline.py. */
+int bvg_timeline_merge(const float* flat, const int64_t* seg_src, const int64_t* seg_dst, const int32_t* seg_n,
+                       const int32_t* seg_rank, int32_t nseg, int64_t max_n, float* out, int64_t total, int32_t normalize, float max_amplitude,
+                       uint32_t* peak_scratch, void* stream);
+
 /* ---- per-op entry points (drop-in for the reference's native extension, and test hooks) ----
  *
  * bvg_activation1d: replaces anti_alias_activation_cuda.forward(x, up_f, down_f, alpha, beta)

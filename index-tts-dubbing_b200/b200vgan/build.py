@@ -10,7 +10,7 @@ PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_DIR = os.path.join(PKG_DIR, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libb200vgan.so")
-SOURCES = ["bvg_api.cu", "bvg_act.cu", "bvg_act2.cu", "bvg_act3.cu", "bvg_conv_simt.cu", "bvg_conv_umma.cu", "bvg_misc.cu", "bvg_ecapa.cu", "bvg_mel.cu"]
+SOURCES = ["bvg_api.cu", "bvg_act.cu", "bvg_act2.cu", "bvg_act3.cu", "bvg_conv_simt.cu", "bvg_conv_umma.cu", "bvg_misc.cu", "bvg_ecapa.cu", "bvg_mel.cu", "bvg_timeline.cu"]
 NVCC_FLAGS = ["-std=c++17", "-O3", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 

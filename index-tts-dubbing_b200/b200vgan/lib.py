@@ -21,7 +21,7 @@ SYMBOLS = [
     "bvg_plan_num_launches", "bvg_forward", "bvg_forward_host", "bvg_activation1d", "bvg_conv1d",
     "bvg_conv_transpose1d", "bvg_forward_ragged", "bvg_plans_created", "bvg_plan_total_frames", "bvg_profile_enable", "bvg_profile_read",
     "bvg_activation1d_packed", "bvg_act_conv1d", "bvg_ecapa_workspace_bytes", "bvg_speaker_embedding",
-    "bvg_forward_pcm16", "bvg_mel_frames", "bvg_log_mel",
+    "bvg_forward_pcm16", "bvg_mel_frames", "bvg_log_mel", "bvg_timeline_merge",
 ]
 
 
@@ -92,6 +92,7 @@ def load(rebuild: bool = False) -> C.CDLL:
     lib.bvg_ecapa_workspace_bytes.restype = sz
     lib.bvg_speaker_embedding.argtypes = [vp, vp, i32, i32, vp, vp, vp, sz, vp]
     lib.bvg_conv_transpose1d.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp]
+    lib.bvg_timeline_merge.argtypes = [vp, vp, vp, vp, vp, i32, C.c_int64, vp, C.c_int64, i32, C.c_float, vp, vp]
     lib.bvg_mel_frames.argtypes = [i32, i32]
     lib.bvg_log_mel.argtypes = [vp, i32, i32, i32, i32, i32, C.c_float, C.c_float, vp, i32, vp]
     _lib = lib

@@ -72,9 +72,51 @@ def prompt_mel():
     return audio.numpy(), mel.transpose(1, 2).contiguous().numpy()
 
 
+def merge_cases():
+    """Random subtitle timelines for the timeline-merge fixture: out-of-order entries, overlaps (3-way too), an empty
+    segment, segments running past the nominal end (array growth), loud sums (peak normalisation)."""
+    rng = np.random.default_rng(77)
+    cases = {}
+    for name, n, sr, span, amp in (("a", 6, 2400, 3.0, 0.3), ("b", 14, 2400, 4.0, 0.9), ("c", 3, 16000, 0.5, 0.5), ("d", 9, 24000, 0.3, 1.2)):
+        st = np.sort(rng.uniform(0.0, span, n))
+        rng.shuffle(st)
+        ln = rng.integers(50, int((0.6 if sr < 10000 else 0.15) * sr), n)
+        if name == "b":
+            ln[3] = 0                                 # empty segment
+            st[5] = st[4] = st[6]                     # identical start times: 3-way overlap
+        en = st + rng.uniform(0.1, 0.5, n)
+        audio = [(amp * rng.standard_normal(int(l))).astype(np.float32) for l in ln]
+        cases[name] = (sr, st, en, audio)
+    return cases
+
+
+def reference_audio_processor():
+    """The unmodified srt_dubbing AudioProcessor; its logging / file-IO dependencies that this image lacks are stubbed."""
+    import types
+    for mod in ("colorama", "soundfile", "tqdm"):
+        try:
+            __import__(mod)
+        except ImportError:
+            m = types.ModuleType(mod)
+            if mod == "colorama":
+                class _C:
+                    def __getattr__(self, k):
+                        return ""
+                m.Fore, m.Back, m.Style = _C(), _C(), _C()
+                m.init = lambda *a, **k: None
+            sys.modules[mod] = m
+    # import the module file itself, not the package __init__ (which pulls the CLI and its text-processing dependencies)
+    for name, path in (("srt_dubbing", os.path.join(REF_ROOT, "srt_dubbing")), ("srt_dubbing.src", os.path.join(REF_ROOT, "srt_dubbing", "src"))):
+        pkg = types.ModuleType(name)
+        pkg.__path__ = [path]
+        sys.modules[name] = pkg
+    import importlib
+    return importlib.import_module("srt_dubbing.src.audio_processor").AudioProcessor
+
+
 def main():
     """`python oracle/gen_golden.py` regenerates everything; `python oracle/gen_golden.py cfg1 prompt` only the
-    named groups (taps, act, amp, ecapa, tiny, cfg1, prompt, logmel).  A full run reproduces the committed files
+    named groups (taps, act, amp, ecapa, tiny, cfg1, prompt, logmel, merge).  A full run reproduces the committed files
     (one torch seed, fixed order); a partial run only touches the named ones (their inputs do not depend on
     the torch random stream)."""
     from b200vgan import synth
@@ -89,6 +131,24 @@ def main():
 
     def want(name):
         return not only or name in only
+
+    # 0. timeline merge of the dubbing tool (srt_dubbing/src/audio_processor.py:133-230) --------
+    if only and "merge" in only or not only:
+        AP = reference_audio_processor()
+        out = {}
+        for name, (sr, st, en, audio) in merge_cases().items():
+            segs = [{"index": i + 1, "start_time": float(st[i]), "end_time": float(en[i]), "audio_data": audio[i]} for i in range(len(st))]
+            ap = AP(sample_rate=sr)
+            out[f"{name}_sr"] = np.int64(sr)
+            out[f"{name}_start"], out[f"{name}_end"] = st, en
+            out[f"{name}_len"] = np.array([len(a) for a in audio], dtype=np.int64)
+            out[f"{name}_audio"] = np.concatenate(audio) if audio else np.zeros(0, np.float32)
+            for flag in (False, True):
+                out[f"{name}_merged_trunc{int(flag)}"] = ap._time_synchronized_merge([dict(s) for s in segs], flag, False)
+            out[f"{name}_natural"] = ap._natural_concatenation([dict(s) for s in segs], False)
+        np.savez_compressed(os.path.join(GOLD, "srt_merge.npz"), **out)
+        if only == ["merge"]:
+            return
 
     # 1. filter taps ------------------------------------------------------------------
     if want("taps"):

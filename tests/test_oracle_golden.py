@@ -128,3 +128,23 @@ def test_cfg1_prompt_fixture_pins_oracle(golden_dir, synth_sd):
     y32 = TC.bigvgan_forward_with_embedding(x, g["emb"], TC.prepare_state_dict(sd))
     assert np.abs(y32 - g["wav"]).max() <= 5e-5        # fp32 summation-order noise (reference's own: fp32_noise)
     assert O.mel_l1(y32[:, 0], g["wav"][:, 0]) <= 1e-4
+
+
+def _merge_cases(golden_dir):
+    g = _g(golden_dir, "srt_merge.npz")
+    for name in ("a", "b", "c", "d"):
+        ln = g[f"{name}_len"]
+        off = np.concatenate([[0], np.cumsum(ln)])
+        segs = [{"index": i + 1, "start_time": float(g[f"{name}_start"][i]), "end_time": float(g[f"{name}_end"][i]),
+                 "audio_data": g[f"{name}_audio"][off[i]:off[i + 1]]} for i in range(len(ln))]
+        yield name, int(g[f"{name}_sr"]), segs, g
+
+
+def test_timeline_merge_oracle_matches_reference(golden_dir):
+    """oracle/srt_merge_oracle.py against the unmodified srt_dubbing AudioProcessor (audio_processor.py:70-230):
+    placement, array growth, the previous-segment overlap rule, fp32 sums and the peak normalisation, bit for bit."""
+    from oracle import srt_merge_oracle as M
+    for name, sr, segs, g in _merge_cases(golden_dir):
+        for flag in (False, True):
+            np.testing.assert_array_equal(M.time_synchronized_merge(segs, sr, flag), g[f"{name}_merged_trunc{int(flag)}"])
+        np.testing.assert_array_equal(M.natural_concatenation(segs), g[f"{name}_natural"])

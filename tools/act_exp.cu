@@ -4,6 +4,8 @@
 #include <vector>
 #include "../index-tts-dubbing_b200/csrc/bvg_act3.cu"
 
+bool bvg_pdl_enabled() { return false; }
+
 int main(int argc, char** argv) {
   const int B = 16;
   const int C = argc > 1 ? atoi(argv[1]) : 24, T = argc > 2 ? atoi(argv[2]) : 240640;
