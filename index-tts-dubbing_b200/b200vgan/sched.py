@@ -230,3 +230,87 @@ def gather_results(res: ShardResult, n_total: int, group=None, device: Optional[
     if missing:
         raise RuntimeError(f"gather_results: segments {missing[:8]} were decoded by no rank")
     return out
+
+
+class LatentHandoff:
+    """Device-resident hand-off between the GPT latent producer and the vocoder.
+
+    Reference: `latent = self.gpt(..., return_latent=True)` (indextts/gpt/model.py:462-488 `get_logits` returns
+    `final_norm(last_hidden_state)[:, :T]`, infer.py:614-619) is a [1, T, 1024] tensor per sentence that the reference
+    hands to `self.bigvgan(latent, ...)` one sentence (or one time-concatenated chunk, infer.py:439-458) at a time,
+    fp32 or autocast-fp16, followed by `.cpu()` per call.
+
+    Contract offered to the producer instead:
+      * layout   rows: ONE persistent [max_rows, gpt_dim] matrix, sentence after sentence ("channels-last" is what
+                 `final_norm` already emits, so `append` is a single strided copy with the dtype cast fused; a producer
+                 that can write in place uses `rows(n)` as its `out=` target and skips even that);
+      * dtype    bf16 by default (what the bf16 mode stores anyway: bit-identical results to fp32 latents), fp16 / fp32 accepted;
+      * stream   everything is ordered on torch's current stream -- no host synchronisation; a producer on another
+                 stream records an event after its last write and the consumer stream waits on it (`wait_event`);
+      * graph    `decode(graph=True)` captures the whole ragged decode (pack -> 234 launches -> int16 PCM) for this
+                 sentence geometry into a CUDA graph on first use and replays it afterwards: the buffers the graph
+                 reads and writes are owned here, so their addresses never change (one launch per decode from the host).
+    """
+
+    def __init__(self, model, max_rows: int, dtype: torch.dtype = torch.bfloat16, int16: bool = True):
+        dev = model.conv_pre.bias.device
+        if dev.type != "cuda":
+            raise RuntimeError("LatentHandoff: the model must live on a CUDA (sm_100) device")
+        self.model, self.int16 = model, int16
+        self.buf = torch.empty(int(max_rows), model._cfg.gpt_dim, device=dev, dtype=dtype)
+        self.out = torch.empty(int(max_rows) * model.hop, device=dev, dtype=torch.int16 if int16 else torch.float32)
+        self.emb = torch.empty(1, 1, model._cfg.speaker_embedding_dim, device=dev, dtype=torch.float32)
+        self.frames: List[int] = []
+        self.used = 0
+        self._graphs: Dict[Tuple[Tuple[int, ...], str], "torch.cuda.CUDAGraph"] = {}
+
+    def reset(self) -> None:
+        self.frames, self.used = [], 0
+
+    def rows(self, n: int) -> torch.Tensor:
+        """The next `n` rows of the hand-off matrix, for a producer that writes its latent in place; counted as one sentence."""
+        if self.used + n > self.buf.shape[0]:
+            raise RuntimeError(f"LatentHandoff: {self.used + n} rows exceed the buffer ({self.buf.shape[0]})")
+        v = self.buf[self.used:self.used + n]
+        self.frames.append(int(n))
+        self.used += int(n)
+        return v
+
+    def append(self, latent: torch.Tensor) -> None:
+        """`latent`: [1, T, gpt_dim] or [T, gpt_dim] on the device (any float dtype): one asynchronous cast-and-copy."""
+        lat = latent[0] if latent.dim() == 3 else latent
+        self.rows(lat.shape[0]).copy_(lat, non_blocking=True)
+
+    def wait_event(self, event: "torch.cuda.Event") -> None:
+        """Order the decode after a producer that ran on another stream."""
+        torch.cuda.current_stream(self.buf.device).wait_event(event)
+
+    @torch.no_grad()
+    def decode(self, emb: torch.Tensor, graph: bool = False) -> List[torch.Tensor]:
+        """Decode every appended sentence as one exact ragged batch.  Returns per-sentence views of the device result
+        vector (int16 PCM, or fp32 with int16=False), valid until the next `decode`."""
+        if not self.frames:
+            return []
+        m, frames = self.model, tuple(self.frames)
+        self.emb.copy_(emb.reshape(1, 1, -1), non_blocking=True)
+        rows, out = self.buf[:self.used], self.out[:self.used * m.hop]
+        if not graph:
+            m.forward_ragged(rows, frames, self.emb, pcm16=self.int16, out=out)
+        else:
+            key = (frames, m.resolved_precision())
+            g = self._graphs.get(key)
+            if g is None:
+                m.forward_ragged(rows, frames, self.emb, pcm16=self.int16, out=out)    # builds the plan, uploads its tables
+                torch.cuda.current_stream(self.buf.device).synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    m.forward_ragged(rows, frames, self.emb, pcm16=self.int16, out=out)
+                if len(self._graphs) >= 32:
+                    self._graphs.pop(next(iter(self._graphs)))
+                self._graphs[key] = g
+            g.replay()
+        res, off = [], 0
+        for n in frames:
+            res.append(out[off * m.hop:(off + n) * m.hop])
+            off += n
+        return res

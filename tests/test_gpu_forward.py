@@ -507,3 +507,40 @@ def test_optional_kernel_paths(env):
     snr = float([ln for ln in out.stdout.splitlines() if ln.startswith("SNR_DB")][-1].split()[1])
     print(env, "cfg1 bf16 SNR dB", snr)
     assert snr >= BF16_SNR_DB
+
+
+def test_latent_handoff_device_resident_and_graph_replay(gen):
+    """bf16 channels-last latents appended on the device, decoded as one ragged batch; the CUDA-graph
+    replay, the eager decode and the decode of the same latents given as fp32 all agree bit for bit (bf16 mode)."""
+    from b200vgan import sched, synth
+    emb = torch.as_tensor(synth.make_speaker_embedding(B=1)).cuda()
+    frames = [9, 31, 4]
+    lat32 = [torch.as_tensor(synth.make_latents(8, i, 1, f)).cuda() for i, f in enumerate(frames)]     # [1, T, 1024] like the GPT's
+    gen.precision = "bf16"
+    h = sched.LatentHandoff(gen, max_rows=64, dtype=torch.bfloat16)
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):                  # the producer runs on its own stream
+        for l in lat32:
+            h.append(l)
+        ev = torch.cuda.Event()
+        ev.record(side)
+    h.wait_event(ev)
+    eager = [w.clone() for w in h.decode(emb)]
+    replay1 = [w.clone() for w in h.decode(emb, graph=True)]     # captures
+    # new latents in the same buffer, same geometry: the replay must see them
+    h.reset()
+    for l in lat32:
+        h.append(2.0 * l)
+    replay2 = [w.clone() for w in h.decode(emb, graph=True)]     # replays
+    eager2 = [w.clone() for w in h.decode(emb)]
+    torch.cuda.synchronize()
+    rows32 = torch.cat([l[0] for l in lat32])
+    direct = gen.forward_ragged(rows32, frames, emb, pcm16=True)
+    off = 0
+    for i, n in enumerate(frames):
+        assert eager[i].dtype == torch.int16 and eager[i].numel() == n * 1024
+        assert torch.equal(eager[i], replay1[i]) and torch.equal(replay2[i], eager2[i])
+        assert torch.equal(eager[i], direct[off * 1024:(off + n) * 1024])
+        assert not torch.equal(eager[i], eager2[i])
+        off += n
+    gen.precision = "fp32"
