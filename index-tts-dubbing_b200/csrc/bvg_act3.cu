@@ -36,7 +36,7 @@
 
 namespace {
 
-constexpr int TWMAX = 224;         // most output rows per stream tile
+constexpr int TWMAX = 240;         // most output rows per stream tile (3 blocks x 8 warps x 8.5 KB = 204 KB of shared memory per SM)
 constexpr int XROWS = TWMAX + 32;  // staged rows per stream: local time -8 .. TW+23
 constexpr int WPB = 8;             // warps per block
 constexpr int MINB = 3;            // resident blocks per SM the kernel is compiled for (<= 85 registers)
@@ -227,7 +227,7 @@ act1d_c8_mma_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __r
         T* rs = region + (size_t)s * XROWS * 8;
         const int r0 = tile0[s] - 8;
 #pragma unroll
-        for (int i = 0; i < XROWS / 32; ++i) {
+        for (int i = 0; i < (XROWS + 31) / 32; ++i) {
           const int r = lane + 32 * i;
           const int row = min(max(r0 + r, 0), L - 1);
           if (r < need && !(BVG_ACT_EXP & 4)) cp_async16(rs + r * 8, xs + (size_t)row * 8);
