@@ -27,6 +27,7 @@
 // per edge tile, ~16 us per launch on short segments) is gone.  Also new: the tile length is chosen per launch
 // (balanced tiles, a whole number of waves when the problem is small), column tiles past a segment's end are
 // not computed, and the storage type is a template parameter (bf16 / fp16).
+#include <cstdio>
 #include <cstdlib>
 #include <type_traits>
 
@@ -371,41 +372,30 @@ act1d_c8_mma_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __r
   if (lane == 0) bulk_wait_read();   // shared memory must stay valid until the last bulk store has read it
 }
 
-// Tile length / tiles per warp for a launch.  Large launches (>= 3 waves of warps): balanced tiles of at most TWMAX
-// rows, two consecutive tiles per warp.  Small launches: the tile count that minimises  waves x (rows per tile +
-// fixed per-tile rows)  -- a short last wave costs a full one, and a launch that fills only part of the GPU gets
-// shorter tiles so that every SM has warps.
+// Tile length / tiles per warp for a launch (measured: tools/gpu_act_tiling.sh, profiles/r2_act_tiling_sweep.txt).
+//   * more than one wave of warps: balanced tiles of at most TWMAX rows (long tiles amortise the 32 halo rows and the
+//     per-tile set-up; between 1 and 8 waves the tile length hardly matters, wave-quantisation models did not predict
+//     the measurements), two consecutive tiles per warp from 8 waves on;
+//   * at most one wave (short segments, small batches): the kernel is bound by one warp's latency, so as many tiles
+//     as still fit one wave (tiles of at least 32 rows).
 struct ActTiling { int tw, ntiles, GT; };
-ActTiling choose_tiling(int max_len, int nchunks, int B, int num_sms) {
-  const long long slots = (long long)num_sms * MINB * WPB;   // resident warps
+ActTiling choose_tiling(int max_len, int nchunks, int B, long long slots /* resident warps on the device */) {
   const int nt_min = (max_len + TWMAX - 1) / TWMAX;
   auto tw_of = [&](int nt) { return ((max_len + nt - 1) / nt + 7) / 8 * 8; };
   auto warps_of = [&](int nt) { return (long long)((nt * nchunks + 1) / 2) * B; };
-  if (warps_of(nt_min) >= 3 * slots) {
-    const int tw = tw_of(nt_min);
-    return ActTiling{tw, (max_len + tw - 1) / tw, 2};
+  int nt = nt_min;
+  if (warps_of(nt_min) <= slots) {
+    const int nt_max = max_len <= 32 ? 1 : (max_len + 31) / 32;
+    while (nt < nt_max && warps_of(nt + 1) <= slots && tw_of(nt + 1) >= 32) ++nt;
   }
-  ActTiling best{tw_of(nt_min), nt_min, 1};
-  double best_cost = 1e30;
-  const int nt_max = max_len <= 32 ? 1 : (max_len + 31) / 32;
-  for (int nt = nt_min; nt <= nt_max && nt <= 8 * nt_min + 8; ++nt) {
-    const int tw = tw_of(nt);
-    if (tw > TWMAX) continue;
-    const int nt_eff = (max_len + tw - 1) / tw;
-    const long long w = warps_of(nt_eff);
-    const long long waves = (w + slots - 1) / slots;
-    // a partially filled single wave runs faster per warp (fewer warps share an SM): proportional above 1/3 full
-    double occ = waves == 1 ? (double)w / (double)slots : 1.0;
-    if (occ < 0.34) occ = 0.34;
-    const double cost = (double)waves * occ * (tw + 40.0);
-    if (cost < best_cost - 1e-9) { best_cost = cost; best = ActTiling{tw, nt_eff, 1}; }
-  }
-  return best;
+  const int tw = tw_of(nt);
+  const int nt_eff = (max_len + tw - 1) / tw;
+  return ActTiling{tw, nt_eff, warps_of(nt_eff) >= 8 * slots ? 2 : 1};
 }
 
 template <typename T>
 cudaError_t launch_t(const ActArgs& a, cudaStream_t s) {
-  static int sms_of_dev[64] = {0};   // per device: SM count and the function attributes
+  static long long sms_of_dev[64] = {0};   // per device: resident warps of this kernel (and the function attributes are set)
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
@@ -415,15 +405,22 @@ cudaError_t launch_t(const ActArgs& a, cudaStream_t s) {
     cudaError_t e = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(act1d_c8_mma_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(act1d_c8_mma_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int per_sm = MINB;
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, act1d_c8_mma_kernel<T, false>, WPB * 32, smem);
     if (e != cudaSuccess) return e;
-    sms_of_dev[dev] = n > 0 ? n : 148;
+    if (per_sm < 1) per_sm = 1;
+    sms_of_dev[dev] = (long long)(n > 0 ? n : 148) * per_sm * WPB;
   }
   const int nchunks = a.C / 8;
   static const int force_tw = [] { const char* e = getenv("BVG_ACT_TW"); return e ? atoi(e) : 0; }();
   ActTiling tl = choose_tiling(a.max_len, nchunks, a.B, sms_of_dev[dev]);
+  static const int force_gt = [] { const char* e = getenv("BVG_ACT_GT"); return e ? atoi(e) : 0; }();
   if (force_tw >= 8 && force_tw <= TWMAX) {
     tl.tw = force_tw / 8 * 8; tl.ntiles = (a.max_len + tl.tw - 1) / tl.tw; tl.GT = tl.ntiles >= 2 ? 2 : 1;
   }
+  if (force_gt == 1 || (force_gt == 2 && tl.ntiles >= 2)) tl.GT = force_gt;
+  static const int dbg = [] { const char* e = getenv("BVG_ACT_DEBUG"); return e ? atoi(e) : 0; }();
+  if (dbg) fprintf(stderr, "act: C %d max_len %d B %d -> tw %d ntiles %d GT %d (resident warps %lld)\n", a.C, a.max_len, a.B, tl.tw, tl.ntiles, tl.GT, sms_of_dev[dev]);
   const int nitems = ((tl.ntiles + tl.GT - 1) / tl.GT) * nchunks;
   dim3 grid((nitems + 2 * WPB - 1) / (2 * WPB), 1, a.B), block(WPB * 32);
   // BVG_ACT_MMA_UPLO=1 adds the rounding residual of the up-FIR taps (a second MMA per column tile): +0.4 dB of SNR
