@@ -163,3 +163,36 @@ def test_gather_world_size_2_gloo():
         p.join(120)
         assert p.exitcode == 0
     assert q.get(timeout=10) is True
+
+
+def test_precision_resolution_follows_autocast(module_cpu):
+    """precision="auto" (constructor default): fp32 like the reference module, the autocast dtype inside an autocast
+    region (infer.py:456, :613); explicit modes are taken as given; anything else is rejected."""
+    from b200vgan import lib
+    m = module_cpu
+    assert m.precision == "auto" and m.resolved_precision() == "fp32" and m._mode() == lib.MODE_FP32
+    for p, mode in (("fp32", lib.MODE_FP32), ("bf16", lib.MODE_BF16), ("fp16", lib.MODE_F16)):
+        m.precision = p
+        assert m.resolved_precision() == p and m._mode() == mode
+    m.precision = "int8"
+    with pytest.raises(lib.BvgError):
+        m.resolved_precision()
+    m.precision = "auto"
+
+
+def test_mel_frontend_constructor_mirrors_reference():
+    """b200vgan.MelSpectrogramFeatures takes the reference's constructor arguments (feature_extractors.py:25-27); only the
+    deployed configuration has a native kernel, and there is no CPU path."""
+    import b200vgan
+    from b200vgan import lib
+    f = b200vgan.MelSpectrogramFeatures()
+    assert (f.sample_rate, f.hop_length, f.n_mels) == (24000, 256, 100)
+    with pytest.raises(ValueError):
+        b200vgan.MelSpectrogramFeatures(padding="valid")
+    for kw in ({"n_fft": 2048}, {"padding": "same"}, {"normalize": True}, {"win_length": 512}):
+        with pytest.raises(lib.BvgError):
+            b200vgan.MelSpectrogramFeatures(**kw)
+    with pytest.raises(lib.BvgError):
+        f(torch.zeros(1, 4000))
+    L = lib.load()
+    assert L.bvg_mel_frames(130560, 256) == 511 and L.bvg_mel_frames(24000, 256) == 94
