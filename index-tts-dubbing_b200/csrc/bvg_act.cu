@@ -134,32 +134,14 @@ act1d_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __restrict
 
 cudaError_t launch_act_c8(const ActArgs& a, int dtype, bool precise, cudaStream_t s) {
   if (a.B <= 0 || a.max_len <= 0) return cudaSuccess;
-  // v2 (warp-autonomous, register-streamed) is the default; BVG_ACT_V1=1 selects the first version
-  // and BVG_ACT_RT=16|32 the rows per thread (A/B knobs used while tuning on the GPU box).
-  static const int use_v1 = [] { const char* e = getenv("BVG_ACT_V1"); return (e && e[0] == '1') ? 1 : 0; }();
+  // 16-bit modes: the tensor-core kernel (both FIRs as warp-level MMAs, bvg_act3.cu).  It is used for EVERY length so that
+  // a segment's samples do not depend on what else is in the batch (the kernels round differently).  fp32 parity mode (and
+  // bf16 with BVG_ACT_MMA=0, a tuning aid): the register-streamed kernel (bvg_act2.cu), BVG_ACT_RT=16|24|32 rows per thread.
   static const int rt = [] { const char* e = getenv("BVG_ACT_RT"); int v = e ? atoi(e) : 32; return (v == 16 || v == 24) ? v : 32; }();
-  // bf16 mode: version 4 (both FIRs on the tensor cores via warp-level MMA, bvg_act3.cu).  Measured on cfg2 (round 1):
-  // 11 % faster than the register-streamed kernel from 15 040 rows per segment on, equal at 3 760, 10 % slower at 940
-  // (coarser work items).  It is used for EVERY length so that a segment's samples do not depend on what else is in
-  // the batch (the two kernels round differently).  BVG_ACT_MMA=0 selects version 3; BVG_ACT_MMA_MINLEN a length threshold.
   static const int use_mma = [] { const char* e = getenv("BVG_ACT_MMA"); return e ? atoi(e) : 1; }();
-  static const int mma_minlen = [] { const char* e = getenv("BVG_ACT_MMA_MINLEN"); return e ? atoi(e) : 1; }();
   if (dtype == 2) return precise ? cudaErrorInvalidValue : launch_act_c8_mma(a, dtype, s);   // fp16 storage: tensor-core kernel only
-  if (use_mma && dtype == 1 && !precise && a.max_len >= mma_minlen) return launch_act_c8_mma(a, dtype, s);
-  if (!use_v1) return launch_act_c8_v2(a, dtype, precise, rt, s);
-  dim3 grid((a.max_len + TR - 1) / TR, a.C / 8, a.B), block(NTHREADS);
-  if (dtype == 0) {
-    if (precise)
-      act1d_kernel<float, false, true><<<grid, block, 0, s>>>((const float*)a.x, (float*)a.y, a.alpha, a.inv_beta, a.seg, a.R, a.C, 0);
-    else
-      act1d_kernel<float, false, false><<<grid, block, 0, s>>>((const float*)a.x, (float*)a.y, a.alpha, a.inv_beta, a.seg, a.R, a.C, 0);
-  } else {
-    if (precise)
-      act1d_kernel<__nv_bfloat16, false, true><<<grid, block, 0, s>>>((const __nv_bfloat16*)a.x, (__nv_bfloat16*)a.y, a.alpha, a.inv_beta, a.seg, a.R, a.C, 0);
-    else
-      act1d_kernel<__nv_bfloat16, false, false><<<grid, block, 0, s>>>((const __nv_bfloat16*)a.x, (__nv_bfloat16*)a.y, a.alpha, a.inv_beta, a.seg, a.R, a.C, 0);
-  }
-  return cudaGetLastError();
+  if (use_mma && dtype == 1 && !precise) return launch_act_c8_mma(a, dtype, s);
+  return launch_act_c8_v2(a, dtype, precise, rt, s);
 }
 
 cudaError_t launch_act_nct(const void* x, void* y, const float* alpha, const float* inv_beta, int B, int C,
