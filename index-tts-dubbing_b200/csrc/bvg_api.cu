@@ -51,6 +51,8 @@ struct ConvLayer {
   float* w_tap = nullptr;   // [ntaps][Cin][N] fp32
   void* w_umma = nullptr;   // bf16 UMMA shared-memory images
   void* w_umma16 = nullptr; // the same images in fp16 (BVG_MODE_F16)
+  void* w_umma_s = nullptr; // 64-column n-tile images (small-batch variant; layers with N >= 256 only), bf16 / fp16
+  void* w_umma16_s = nullptr;
   void setup() {
     if (!transposed) {
       ntaps = k; N = Cout; u = 1; p = 0; q_extra = 0;
@@ -114,6 +116,7 @@ struct bvg_handle {
   std::vector<TableChunk> tab_chunks;
   std::map<size_t, std::vector<std::pair<char*, char*>>> tab_free;   // slice bytes -> (device, host) slices
   int64_t plans_created = 0;
+  int num_sms = 148;
   bool finalized = false;
   int launch_counter = 0;   // kernel launches issued by the forward in progress
   // optional per-launch CUDA-event timing (bench.py's roofline numbers)
@@ -214,6 +217,16 @@ ConvArgs make_conv_args(const ConvLayer& L, const bvg_plan* p, int gin, int gout
   a.x = x; a.y = y; a.res = res;
   a.dtype = p->dtype;
   a.w = umma ? (const void*)(p->dtype == 2 ? L.w_umma16 : L.w_umma) : (const void*)L.w_tap;
+  if (umma && L.w_umma_s && !act) {
+    // small-batch variant: with 256-column n-tiles this layer would occupy fewer than half of the SMs
+    const int ti1 = (gin * 3 + 0) * 2 + (L.q_extra ? 1 : 0);
+    const int nt_big = (L.N + 255) / 256;
+    static const int allow = [] { const char* e = getenv("BVG_CONV_SMALL"); return e ? atoi(e) : 1; }();
+    if (allow && (long long)p->total_mt[ti1] * nt_big * 2 <= p->h->num_sms) {
+      a.bn_small = 1;
+      a.w = p->dtype == 2 ? L.w_umma16_s : L.w_umma_s;
+    }
+  }
   a.bias = bias; a.bias_bstride = bias_bstride;
   a.acc_img_scale = (float)p->h->nk;
   a.seg_in = p->seg_dev + (size_t)gin * p->B;
@@ -326,6 +339,7 @@ int bvg_create(const bvg_config* cfg, bvg_handle** out) {
   bvg_handle* h = new bvg_handle();
   h->cfg = *cfg;
   CK(cudaGetDevice(&h->device));
+  CK(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device));
   h->nups = nups; h->nk = nk; h->nd = nd;
   const int C0 = cfg->upsample_initial_channel, D = cfg->speaker_embedding_dim;
 
@@ -459,8 +473,14 @@ static int finalize_conv(bvg_handle* h, ConvLayer& L, cudaStream_t s, bool want_
       if (!L.w_umma16) {
         if (dev_alloc(h, &L.w_umma16, bytes)) return 1;
       }
-      CK(launch_repack_umma(L.w_tap, L.w_umma, 1, L.ntaps, L.Cin, L.N, (float)h->nk, s));
-      CK(launch_repack_umma(L.w_tap, L.w_umma16, 2, L.ntaps, L.Cin, L.N, (float)h->nk, s));
+      CK(launch_repack_umma(L.w_tap, L.w_umma, 1, L.ntaps, L.Cin, L.N, (float)h->nk, false, s));
+      CK(launch_repack_umma(L.w_tap, L.w_umma16, 2, L.ntaps, L.Cin, L.N, (float)h->nk, false, s));
+      const size_t sbytes = L.N >= 256 ? umma_weight_image_bytes(L.ntaps, L.Cin, L.N, true) : 0;
+      if (sbytes) {
+        if (!L.w_umma_s && (dev_alloc(h, &L.w_umma_s, sbytes) || dev_alloc(h, &L.w_umma16_s, sbytes))) return 1;
+        CK(launch_repack_umma(L.w_tap, L.w_umma_s, 1, L.ntaps, L.Cin, L.N, (float)h->nk, true, s));
+        CK(launch_repack_umma(L.w_tap, L.w_umma16_s, 2, L.ntaps, L.Cin, L.N, (float)h->nk, true, s));
+      }
     }
   }
   return 0;
@@ -886,6 +906,14 @@ int conv_op(bool transposed, const float* x, const float* w, const float* bias, 
     }
   }
   if (mode != BVG_MODE_FP32) {
+    if (!a.act_alpha && L.N >= 256) {   // same rule as bvg_forward: the small-batch variant when few CTAs would run
+      int dev = 0, sms = 148;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      static const int allow = [] { const char* e = getenv("BVG_CONV_SMALL"); return e ? atoi(e) : 1; }();
+      const long long mt1 = (long long)B * ((T + L.q_extra + 127) / 128);
+      if (allow && mt1 * ((L.N + 255) / 256) * 2 <= sms) a.bn_small = 1;
+    }
     if (!a.act_alpha) a.msub = conv_umma_default_msub(a);
     std::vector<int> pf(B + 1, 0);
     for (int b = 0; b < B; ++b) pf[b + 1] = pf[b] + (T + L.q_extra + 128 * a.msub - 1) / (128 * a.msub);
@@ -894,10 +922,10 @@ int conv_op(bool transposed, const float* x, const float* w, const float* bias, 
     CK(cudaMemcpyAsync(pf_dev, pf.data(), pf.size() * sizeof(int), cudaMemcpyHostToDevice, s));
     CK(cudaStreamSynchronize(s));
     a.tile_prefix = pf_dev; a.total_mt = pf[B];
-    size_t bytes = umma_weight_image_bytes(L.ntaps, Cin, L.N);
+    size_t bytes = umma_weight_image_bytes(L.ntaps, Cin, L.N, a.bn_small != 0);
     if (!bytes || !conv_umma_supported(a)) return fail("conv op: shape not supported by the tcgen05 kernel");
     if (tmp.alloc(&wu, bytes)) return 1;
-    CK(launch_repack_umma(wt, wu, dt, L.ntaps, Cin, L.N, 1.f, s));
+    CK(launch_repack_umma(wt, wu, dt, L.ntaps, Cin, L.N, 1.f, a.bn_small != 0, s));
     a.w = wu;
     CK(launch_conv_umma(a, s));
   } else {

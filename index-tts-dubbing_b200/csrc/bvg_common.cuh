@@ -52,6 +52,7 @@ struct ConvArgs {
   const int* tile_prefix;   // [B+1] prefix sum of tiles per segment (device)
   int total_mt;             // tile_prefix[B]
   int msub;                 // 1, 2 or 4
+  int bn_small;             // 1: `w` is the 64-column n-tile image (small-batch variant of a wide layer), msub must be 1
   // fused Activation1d (tcgen05 kernel, bf16): when set, x is the RAW input and the kernel applies the
   // activation with these per-input-channel parameters while staging its A operand
   const float* act_alpha;

@@ -82,8 +82,10 @@ inline int env_int(const char* name, int dflt) {
   return e ? atoi(e) : dflt;
 }
 
-// Tiling that only depends on the layer (the weight image layout depends on it).
-inline UmmaTiling make_tiling(int ntaps, int Cin, int N) {
+// Tiling that only depends on the layer (the weight image layout depends on it).  `small`: 64-column n-tiles -- the
+// small-batch variant of the wide layers: with only a few m-tiles (one short utterance) a 256-column n-tile leaves
+// 3-12 CTAs streaming 4-13 MB of weights each; four times as many CTAs stream a quarter each.
+inline UmmaTiling make_tiling(int ntaps, int Cin, int N, bool small = false) {
   UmmaTiling t{};
   t.ok = false;
   if (Cin % 8 || N % 8 || ntaps < 1 || ntaps > BVG_MAX_TAPS) return t;
@@ -93,7 +95,8 @@ inline UmmaTiling make_tiling(int ntaps, int Cin, int N) {
   else return t;
   // N tile: 256 columns by default -- a 128 x 256 x 16 MMA is the only cta_group::1 shape that runs at
   // the tensor-pipe floor (tools/umma_bench.cu) and it halves the A-tile re-reads per output column.
-  static const int bnmax = [] { int v = env_int("BVG_CONV_BNMAX", 256); return (v == 128 || v == 192) ? v : 256; }();
+  static const int bnmax_env = [] { int v = env_int("BVG_CONV_BNMAX", 256); return (v == 128 || v == 192) ? v : 256; }();
+  const int bnmax = small ? 64 : bnmax_env;
   const int n_pad = round_up_i(N, 16);
   t.NT = (n_pad + bnmax - 1) / bnmax;
   t.BN = round_up_i((n_pad + t.NT - 1) / t.NT, 16);
@@ -977,7 +980,7 @@ void tap_range(const ConvArgs& a, int& mn, int& mx) {
 // Launch-time configuration for a given number of 128-row sub-tiles per tile.
 bool configure(const ConvArgs& a, int msub, UmmaKernelArgs& ka, size_t& smem_bytes) {
   const int N = a.u * a.Cout;
-  const UmmaTiling t = make_tiling(a.ntaps, a.Cin, N);
+  const UmmaTiling t = make_tiling(a.ntaps, a.Cin, N, a.bn_small != 0);
   if (!t.ok) return false;
   int mn, mx;
   tap_range(a, mn, mx);
@@ -1088,8 +1091,8 @@ bool configure_fused(const ConvArgs& a, int msub, UmmaKernelArgs& ka, size_t& sm
 
 }  // namespace
 
-size_t umma_weight_image_bytes(int ntaps, int Cin, int N) {
-  UmmaTiling t = make_tiling(ntaps, Cin, N);
+size_t umma_weight_image_bytes(int ntaps, int Cin, int N, bool small) {
+  UmmaTiling t = make_tiling(ntaps, Cin, N, small);
   if (!t.ok) return 0;
   return (size_t)(t.NT * t.NKB * ntaps + (has_identity(t, Cin, N) ? 2 * t.NKB : 0)) * t.KC * t.BN * 16;
 }
@@ -1108,8 +1111,8 @@ static void repack_umma_t(const float* wp_tap_major, T* img, const UmmaTiling& t
 }
 
 cudaError_t launch_repack_umma(const float* wp_tap_major, void* img, int dtype, int ntaps, int Cin, int N, float acc_img_scale,
-                               cudaStream_t s) {
-  UmmaTiling t = make_tiling(ntaps, Cin, N);
+                               bool small, cudaStream_t s) {
+  UmmaTiling t = make_tiling(ntaps, Cin, N, small);
   if (!t.ok || (dtype != 1 && dtype != 2)) return cudaErrorInvalidValue;
   if (dtype == 1) repack_umma_t(wp_tap_major, (__nv_bfloat16*)img, t, ntaps, Cin, N, acc_img_scale, s);
   else repack_umma_t(wp_tap_major, (__half*)img, t, ntaps, Cin, N, acc_img_scale, s);
@@ -1120,6 +1123,7 @@ cudaError_t launch_repack_umma(const float* wp_tap_major, void* img, int dtype, 
 // fit the shared-memory budget; small problems keep small tiles so all SMs get work.
 int conv_umma_default_msub(const ConvArgs& a) {
   static const int forced = env_int("BVG_CONV_MSUB", 0);
+  if (a.bn_small) return 1;   // the small-batch variant exists to maximise the number of CTAs
   const UmmaTiling t = make_tiling(a.ntaps, a.Cin, a.u * a.Cout);
   if (!t.ok) return 1;
   for (int msub = 4; msub >= 2; msub >>= 1) {
@@ -1139,7 +1143,7 @@ int conv_umma_fused_msub(const ConvArgs& a, bool force) {
   // activation is FP32-pipe bound and 10 activation warps per SM cannot outrun the stand-alone kernel.
   static const int enabled = env_int("BVG_FUSE_ACT", 0);
   static const int forced = env_int("BVG_CONV_MSUB", 0);
-  if (!(enabled || force) || !a.act_alpha || a.dtype == 2) return 0;   // the fused activation warps are bf16 only
+  if (!(enabled || force) || !a.act_alpha || a.dtype == 2 || a.bn_small) return 0;   // the fused activation warps are bf16 only
   const UmmaTiling t = make_tiling(a.ntaps, a.Cin, a.Cout);
   if (!t.ok || t.NT != 1 || a.u != 1) return 0;
   for (int msub = 4; msub >= 1; msub >>= 1) {

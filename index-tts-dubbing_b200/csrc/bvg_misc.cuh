@@ -17,9 +17,10 @@ cudaError_t launch_repack_convt(const float* w, float* wp, int Cin, int Cout, in
 cudaError_t launch_snake_params(const float* la, const float* lb, float* alpha, float* inv_beta, int n,
                                 cudaStream_t s);
 // 16-bit UMMA weight images (bvg_conv_umma.cu); dtype 1 = bf16, 2 = fp16
-size_t umma_weight_image_bytes(int ntaps, int Cin, int N);
+// small: the 64-column n-tile images of the small-batch variant (wide layers only)
+size_t umma_weight_image_bytes(int ntaps, int Cin, int N, bool small = false);
 cudaError_t launch_repack_umma(const float* wp_tap_major, void* img, int dtype, int ntaps, int Cin, int N, float acc_img_scale,
-                               cudaStream_t s);
+                               bool small, cudaStream_t s);
 cudaError_t launch_zero_guards(void* buf, int esize, const SegDesc* seg, int B, int C, int R, cudaStream_t s);
 // every packed buffer of a plan in one launch
 struct GuardJob { void* buf; const SegDesc* seg; int chunks, R, vec_per_row; };
