@@ -17,7 +17,8 @@
 // only in registers.  Operand movement: ldmatrix.trans turns the staged [time][8 channels] rows into A
 // fragments, stmatrix.trans writes the result rows back.  The up-FIR runs in the storage type (its A operand
 // is the stored tensor; taps rounded to it, optionally split hi + lo, BVG_ACT_MMA_UPLO=1); the down-FIR runs in
-// fp16 (activated samples and taps rounded to 11 bits, saturating).
+// fp16 (activated samples and taps rounded to 11 bits, saturating); its K-steps are offset by half a step against the output
+// column tiles, so that 8 outputs need two K-steps of activated samples, not three.
 //
 // Formulas:  u[m] = 2 sum_k f[k] x[(m+5-k)/2],  y[t] = sum_k f[k] s[clamp(2t+k-5, 0, 2L-1)],
 // with replicate padding of the input (staged rows are clamped to the segment) AND of the activated 2x signal.
@@ -173,12 +174,14 @@ act1d_c8_mma_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __r
     gup_hi[half] = pack_io<T>(h0, h1);
     gup_lo[half] = pack_io<T>(v0 - h0, v1 - h1);
   }
-  uint32_t fdn[3][2];                                 // down-FIR: B_d[k][n] = f[16 d + k - 2n + 5], d = -1, 0, +1, as fp16
+  // down-FIR: K-step J' holds the activated samples 16J'-8 .. 16J'+7 (column tiles 2J'-1 and 2J'), so the 8 outputs of
+  // column tile J (samples 16J-5 .. 16J+20) need exactly the two K-steps J and J+1:  B_d[k][n] = f[16 d + k - 2n - 3], d = 0, 1 (fp16)
+  uint32_t fdn[2][2];
 #pragma unroll
-  for (int d = 0; d < 3; ++d)
+  for (int d = 0; d < 2; ++d)
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
-      const int k0 = 2 * t + 8 * half, off = 16 * (d - 1) + 5 - 2 * g;
+      const int k0 = 2 * t + 8 * half, off = 16 * d - 3 - 2 * g;
       fdn[d][half] = pack_f16(tap(k0 + off), tap(k0 + 1 + off));
     }
   float a2[2], hh[2];
@@ -208,7 +211,7 @@ act1d_c8_mma_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __r
     const int nrmax = max(nrow[0], nrow[1]);
     if (nrmax <= 0) break;
     const int nJ = (nrmax + 7) >> 3;          // output column tiles to compute
-    const int need = 8 * nJ + 32;             // staged rows the main pass reads (local time -8 .. 8 nJ + 23)
+    const int need = 8 * nJ + 24;             // staged rows the main pass reads (local time -8 .. 8 nJ + 15)
     // ---- stage the raw rows: region row r of stream s = x[clamp(tile0 - 8 + r, 0, L-1)] (replicate padding of the input).
     //      Interior tiles (no clamping, both streams present): ONE bulk copy per stream, issued by lane 0 ----
     const bool interior = have[1] && tile0[0] >= 8 && tile0[1] >= 8 && tile0[0] - 8 + need <= L && tile0[1] - 8 + need <= L;
@@ -272,21 +275,20 @@ act1d_c8_mma_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __r
       v[0] = fmaf(-hh[0], __cosf(a2[0] * c[0]), c[0]); v[1] = fmaf(-hh[0], __cosf(a2[0] * c[1]), c[1]);
       v[2] = fmaf(-hh[1], __cosf(a2[1] * c[2]), c[2]); v[3] = fmaf(-hh[1], __cosf(a2[1] * c[3]), c[3]);
     };
-    auto down = [&](int J, const uint32_t (&P)[4], const uint32_t (&C)[4], const uint32_t (&N)[4]) {
+    auto down = [&](int J, const uint32_t (&C)[4], const uint32_t (&N)[4]) {
       float c[4];
       if (BVG_ACT_EXP & 2) {
-        c[0] = __uint_as_float(P[2] ^ C[0] ^ N[0]); c[1] = __uint_as_float(P[3] ^ C[1] ^ N[1]);
+        c[0] = __uint_as_float(C[0] ^ N[0]); c[1] = __uint_as_float(C[1] ^ N[1]);
         c[2] = __uint_as_float(C[2] ^ N[2]); c[3] = __uint_as_float(C[3] ^ N[3]);
       } else {
-      mma16816<__half>(c, P, fdn[0][0], fdn[0][1], hh[0], hh[0], hh[1], hh[1]);
-      mma16816<__half>(c, C, fdn[1][0], fdn[1][1], c[0], c[1], c[2], c[3]);
-      mma16816<__half>(c, N, fdn[2][0], fdn[2][1], c[0], c[1], c[2], c[3]);
+        mma16816<__half>(c, C, fdn[0][0], fdn[0][1], hh[0], hh[0], hh[1], hh[1]);
+        mma16816<__half>(c, N, fdn[1][0], fdn[1][1], c[0], c[1], c[2], c[3]);
       }
-      // the raw rows these outputs overwrite were consumed by the column tiles above
+      // the raw rows these outputs overwrite (region rows 8J+8 .. 8J+15) were consumed by column tiles <= 2J+2; later
+      // column tiles start at region row 8J+17
       stsm_x2_trans(st_base + (uint32_t)(8 * J) * 16, pack_io<T>(c[0], c[1]), pack_io<T>(c[2], c[3]));
     };
-    uint32_t ap[4], ac[4], an[4];   // down-FIR A fragments of K-steps J-1, J, J+1 (16 activated samples each)
-    ap[0] = ap[1] = 0u;             // samples -16 .. -9 are never used (zero taps): skip their column tile
+    uint32_t ka[4], kb[4];   // down-FIR A fragments of two consecutive K-steps: {tile 2J'-1: stream 0, stream 1, tile 2J': stream 0, stream 1}
 
     if (!edge) {
       auto up_tile = [&](int j, uint32_t& p0, uint32_t& p1) {
@@ -295,25 +297,22 @@ act1d_c8_mma_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __r
         p0 = pack_f16(v[0], v[1]);   // fp16 keeps 11 bits of the activated sample (bf16: 8); its range is ample for activations
         p1 = pack_f16(v[2], v[3]);
       };
-      up_tile(-1, ap[2], ap[3]);
-      up_tile(0, ac[0], ac[1]);
-      up_tile(1, ac[2], ac[3]);
-      // one output column tile J (rows 8J .. 8J+7 of both streams); P / C / N = K-steps J-1, J, J+1 (N is produced here)
-      auto step = [&](int J, const uint32_t (&P)[4], const uint32_t (&C)[4], uint32_t (&N)[4]) {
-        up_tile(2 * J + 2, N[0], N[1]);
-        up_tile(2 * J + 3, N[2], N[3]);
-        down(J, P, C, N);
+      up_tile(-1, ka[0], ka[1]);
+      up_tile(0, ka[2], ka[3]);
+      // one output column tile J (rows 8J .. 8J+7 of both streams): C = K-step J, N = K-step J+1 (produced here)
+      auto step = [&](int J, const uint32_t (&C)[4], uint32_t (&N)[4]) {
+        up_tile(2 * J + 1, N[0], N[1]);
+        up_tile(2 * J + 2, N[2], N[3]);
+        down(J, C, N);
       };
-      // the J loop is unrolled by 3 with rotating fragment names; the remaining one or two column tiles follow
+      // the J loop is unrolled by 2 with alternating fragment names; an odd last column tile follows
       int J = 0;
 #pragma unroll 1
-      for (; J + 3 <= nJ; J += 3) {
-        step(J, ap, ac, an);
-        step(J + 1, ac, an, ap);
-        step(J + 2, an, ap, ac);
+      for (; J + 2 <= nJ; J += 2) {
+        step(J, ka, kb);
+        step(J + 1, kb, ka);
       }
-      if (J < nJ) step(J, ap, ac, an);
-      if (J + 1 < nJ) step(J + 1, ac, an, ap);
+      if (J < nJ) step(J, ka, kb);
     } else {
       // Tiles at a segment end: replicate padding of the ACTIVATED signal.  Column tiles are produced in increasing
       // order, so the last in-segment sample s[hi] (column tile hi >> 3) is known before any sample beyond it.
@@ -332,7 +331,7 @@ act1d_c8_mma_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __r
           if (m0 + 1 > hi[s]) v[2 * s + 1] = e[s];
         }
       };
-      float v0[4], vm[4], v1[4];
+      float v0[4], vm[4];
       up_edge(0, v0);
       up_vals(-1, vm);
 #pragma unroll
@@ -341,20 +340,18 @@ act1d_c8_mma_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __r
         if (tile0[s] == 0) vm[2 * s] = vm[2 * s + 1] = first;
         else if (hi[s] < 0) vm[2 * s] = vm[2 * s + 1] = 0.f;   // stream past its segment: nothing is stored
       }
-      up_edge(1, v1);
-      ap[2] = pack_f16(vm[0], vm[1]); ap[3] = pack_f16(vm[2], vm[3]);
-      ac[0] = pack_f16(v0[0], v0[1]); ac[1] = pack_f16(v0[2], v0[3]);
-      ac[2] = pack_f16(v1[0], v1[1]); ac[3] = pack_f16(v1[2], v1[3]);
+      ka[0] = pack_f16(vm[0], vm[1]); ka[1] = pack_f16(vm[2], vm[3]);
+      ka[2] = pack_f16(v0[0], v0[1]); ka[3] = pack_f16(v0[2], v0[3]);
 #pragma unroll 1
       for (int J = 0; J < nJ; ++J) {
         float va[4], vb[4];
-        up_edge(2 * J + 2, va);
-        up_edge(2 * J + 3, vb);
-        an[0] = pack_f16(va[0], va[1]); an[1] = pack_f16(va[2], va[3]);
-        an[2] = pack_f16(vb[0], vb[1]); an[3] = pack_f16(vb[2], vb[3]);
-        down(J, ap, ac, an);
+        up_edge(2 * J + 1, va);
+        up_edge(2 * J + 2, vb);
+        kb[0] = pack_f16(va[0], va[1]); kb[1] = pack_f16(va[2], va[3]);
+        kb[2] = pack_f16(vb[0], vb[1]); kb[3] = pack_f16(vb[2], vb[3]);
+        down(J, ka, kb);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { ap[i] = ac[i]; ac[i] = an[i]; }
+        for (int i = 0; i < 4; ++i) ka[i] = kb[i];
       }
     }
     // ---- copy the result rows out: one bulk store per stream (the rows are contiguous in the packed layout) ----
