@@ -126,8 +126,10 @@ __device__ __forceinline__ float tap(int k) {   // f[k], 0 outside 0..11 (kaiser
   return f[k < 6 ? k : 11 - k];
 }
 
-// UP_LO: add the rounding residual of the up-FIR taps as a second MMA per column tile
-template <typename T, bool UP_LO>
+// UP_LO: add the rounding residual of the up-FIR taps as a second MMA per column tile.
+// PRE: the input is pre-scaled by 2 alpha per channel (u' = 2 alpha u comes straight out of the up-FIR), the output stays
+// scaled:  v = u' - (2 alpha h) cos(u') = 2 alpha (s - h),  y' = down(v) + 2 alpha h = 2 alpha y  -- one multiply per sample less.
+template <typename T, bool UP_LO, bool PRE = false>
 __global__ void __launch_bounds__(WPB * 32, MINB)
 act1d_c8_mma_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __restrict__ alpha,
                     const float* __restrict__ inv_beta, const SegDesc* __restrict__ seg, int R, int ntiles, int nchunks,
@@ -189,6 +191,7 @@ act1d_c8_mma_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __r
   for (int s = 0; s < 2; ++s) {
     a2[s] = 2.f * alpha[chunk[s] * 8 + g];
     hh[s] = 0.5f * inv_beta[chunk[s] * 8 + g];
+    if (PRE) hh[s] *= a2[s];   // 2 alpha h
   }
   const uint32_t reg_s = smem_addr(region);
   // ldmatrix row address of this lane: matrices 0..3 = (stream 0, rows +0..7), (stream 1, +0..7), (stream 0, +8..15), (stream 1, +8..15)
@@ -270,6 +273,11 @@ act1d_c8_mma_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __r
       if (BVG_ACT_EXP & 1) {
         v[0] = fmaf(-hh[0], a2[0] * c[0], c[0]); v[1] = fmaf(-hh[0], a2[0] * c[1], c[1]);
         v[2] = fmaf(-hh[1], a2[1] * c[2], c[2]); v[3] = fmaf(-hh[1], a2[1] * c[3], c[3]);
+        return;
+      }
+      if (PRE) {
+        v[0] = fmaf(-hh[0], __cosf(c[0]), c[0]); v[1] = fmaf(-hh[0], __cosf(c[1]), c[1]);
+        v[2] = fmaf(-hh[1], __cosf(c[2]), c[2]); v[3] = fmaf(-hh[1], __cosf(c[3]), c[3]);
         return;
       }
       v[0] = fmaf(-hh[0], __cosf(a2[0] * c[0]), c[0]); v[1] = fmaf(-hh[0], __cosf(a2[0] * c[1]), c[1]);
@@ -402,6 +410,7 @@ cudaError_t launch_t(const ActArgs& a, cudaStream_t s) {
     cudaError_t e = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(act1d_c8_mma_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(act1d_c8_mma_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(act1d_c8_mma_kernel<T, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int per_sm = MINB;
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, act1d_c8_mma_kernel<T, false>, WPB * 32, smem);
     if (e != cudaSuccess) return e;
@@ -423,6 +432,9 @@ cudaError_t launch_t(const ActArgs& a, cudaStream_t s) {
   // BVG_ACT_MMA_UPLO=1 adds the rounding residual of the up-FIR taps (a second MMA per column tile): +0.4 dB of SNR
   // on config 1 in the bf16 mode for ~4 % of the step time; off by default.
   static const int up_lo = [] { const char* e = getenv("BVG_ACT_MMA_UPLO"); return e ? atoi(e) : 0; }();
+  if (a.prescaled)   // (the hi + lo tap split is a bf16-accuracy aid of the plain variant only)
+    return launch_pdl(act1d_c8_mma_kernel<T, false, true>, grid, block, smem, s, (const T*)a.x, (T*)a.y, a.alpha, a.inv_beta, a.seg, a.R,
+                      tl.ntiles, nchunks, tl.tw, tl.GT);
   if (!up_lo)
     return launch_pdl(act1d_c8_mma_kernel<T, false>, grid, block, smem, s, (const T*)a.x, (T*)a.y, a.alpha, a.inv_beta, a.seg, a.R,
                       tl.ntiles, nchunks, tl.tw, tl.GT);

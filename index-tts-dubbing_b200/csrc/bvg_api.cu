@@ -8,6 +8,7 @@
 //   * the residual add  xt + x  (models.py:72) and the resblock mean  xs / 3  (models.py:237-243)
 //     folded into the epilogue of each block's last convolution.
 #include <cstdarg>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -53,6 +54,10 @@ struct ConvLayer {
   void* w_umma16 = nullptr; // the same images in fp16 (BVG_MODE_F16)
   void* w_umma_s = nullptr; // 64-column n-tile images (small-batch variant; layers with N >= 256 only), bf16 / fp16
   void* w_umma16_s = nullptr;
+  // 16-bit modes: per-channel factors folded into the UMMA images (see fold_activation_scales) and the matching bias
+  const float* fold_out = nullptr;   // [Cout]
+  const float* fold_in = nullptr;    // [Cin]
+  float* bias_umma = nullptr;        // bias * fold_out (used instead of `bias` by the tcgen05 path)
   void setup() {
     if (!transposed) {
       ntaps = k; N = Cout; u = 1; p = 0; q_extra = 0;
@@ -68,6 +73,8 @@ struct ConvLayer {
 struct ActLayer {
   int C = 0;
   float *la = nullptr, *lb = nullptr, *alpha = nullptr, *inv_beta = nullptr;
+  float *s2a = nullptr, *inv_s2a = nullptr;   // 2 alpha and its reciprocal (device, [C]) when the layer is pre-scaled
+  bool prescaled = false;   // 16-bit modes: input / output carry the factor 2 alpha, folded into the neighbouring convolutions
 };
 
 struct CondLayer {
@@ -256,7 +263,8 @@ int run_conv(const ConvLayer& L, const bvg_plan* p, int gin, int gout, const voi
   const double flops = 2.0 * L.Cin * L.ntaps * L.N * (double)p->sumlen[gin];
   const double bytes = ((double)L.Cin * p->sumlen[gin] + (double)L.Cout * p->sumlen[gout] * (res ? 2 : 1)) * p->esize;
   if (p->mode != BVG_MODE_FP32 && L.w_umma) {
-    ConvArgs a = make_conv_args(L, p, gin, gout, x, y, res, bias, bias_bstride, scale, accumulate, true);
+    const float* ubias = (L.bias_umma && bias == L.bias) ? L.bias_umma : bias;   // the image's output channels are pre-scaled
+    ConvArgs a = make_conv_args(L, p, gin, gout, x, y, res, ubias, bias_bstride, scale, accumulate, true);
     if (conv_umma_supported(a)) {
       ProfScope ps(p->h, s, PROF_CONV_TC, flops, bytes);
       CK(launch_conv_umma(a, s));
@@ -295,6 +303,7 @@ int run_act_conv(const ActLayer& A, const ConvLayer& L, const bvg_plan* p, int g
 
 int run_act(const ActLayer& A, const bvg_plan* p, int g, const void* x, void* y, cudaStream_t s) {
   ActArgs aa{x, y, A.alpha, A.inv_beta, p->seg_dev + (size_t)g * p->B, p->R[g], p->C[g], p->B, p->maxlen[g]};
+  aa.prescaled = (A.prescaled && p->mode != BVG_MODE_FP32) ? 1 : 0;
   // algorithmic bytes of a standalone Activation1d launch: read + write of every valid element
   const double bytes = 2.0 * p->C[g] * (double)p->sumlen[g] * p->esize;
   ProfScope ps(p->h, s, PROF_ACT, 0.0, bytes);
@@ -473,13 +482,21 @@ static int finalize_conv(bvg_handle* h, ConvLayer& L, cudaStream_t s, bool want_
       if (!L.w_umma16) {
         if (dev_alloc(h, &L.w_umma16, bytes)) return 1;
       }
-      CK(launch_repack_umma(L.w_tap, L.w_umma, 1, L.ntaps, L.Cin, L.N, (float)h->nk, false, s));
-      CK(launch_repack_umma(L.w_tap, L.w_umma16, 2, L.ntaps, L.Cin, L.N, (float)h->nk, false, s));
+      CK(launch_repack_umma(L.w_tap, L.w_umma, 1, L.ntaps, L.Cin, L.N, (float)h->nk, false, s, L.fold_out, L.fold_in));
+      CK(launch_repack_umma(L.w_tap, L.w_umma16, 2, L.ntaps, L.Cin, L.N, (float)h->nk, false, s, L.fold_out, L.fold_in));
+      if (L.fold_out) {
+        if (!L.bias_umma) {
+          void* pb = nullptr;
+          if (dev_alloc(h, &pb, (size_t)L.Cout * sizeof(float))) return 1;
+          L.bias_umma = (float*)pb;
+        }
+        CK(launch_scale_vec(L.bias, L.fold_out, L.bias_umma, L.Cout, s));
+      }
       const size_t sbytes = L.N >= 256 ? umma_weight_image_bytes(L.ntaps, L.Cin, L.N, true) : 0;
       if (sbytes) {
         if (!L.w_umma_s && (dev_alloc(h, &L.w_umma_s, sbytes) || dev_alloc(h, &L.w_umma16_s, sbytes))) return 1;
-        CK(launch_repack_umma(L.w_tap, L.w_umma_s, 1, L.ntaps, L.Cin, L.N, (float)h->nk, true, s));
-        CK(launch_repack_umma(L.w_tap, L.w_umma16_s, 2, L.ntaps, L.Cin, L.N, (float)h->nk, true, s));
+        CK(launch_repack_umma(L.w_tap, L.w_umma_s, 1, L.ntaps, L.Cin, L.N, (float)h->nk, true, s, L.fold_out, L.fold_in));
+        CK(launch_repack_umma(L.w_tap, L.w_umma16_s, 2, L.ntaps, L.Cin, L.N, (float)h->nk, true, s, L.fold_out, L.fold_in));
       }
     }
   }
@@ -497,17 +514,59 @@ static int finalize_act(bvg_handle* h, ActLayer& A, cudaStream_t s) {
   return 0;
 }
 
+// 16-bit modes: the SECOND activation of every AMPBlock1 step (models.py:69-72: xt = c1(act1(x)); xt = c2(act2(xt))) reads a
+// tensor only it consumes (c1's output) and writes one only c2 consumes.  Folding 2 alpha per channel into c1's output
+// channels (weights and bias) and 1 / (2 alpha) into c2's input channels lets that activation run "pre-scaled": the up-FIR
+// delivers the cosine's argument directly, one multiply per activated sample less (bvg_act3.cu, PRE).  The fold happens in
+// fp32 before the images are rounded; a layer whose alpha leaves [1/64, 64] keeps the plain kernel (fp16 range).  The fp32
+// parity mode, the per-op entry points and the experimental fused kernel use the unfolded parameters.
+static int fold_activation_scales(bvg_handle* h, cudaStream_t s) {
+  static const int enabled = [] {
+    const char* e = getenv("BVG_ACT_FOLD");
+    const char* f = getenv("BVG_FUSE_ACT");   // the experimental fused kernel and the register-streamed kernel
+    const char* m = getenv("BVG_ACT_MMA");    // (BVG_ACT_MMA=0) have no pre-scaled variant
+    return (e ? atoi(e) != 0 : true) && !(f && atoi(f)) && !(m && !atoi(m));
+  }();
+  std::vector<float> host;
+  for (size_t rb = 0; rb < (size_t)h->nups * h->nk; ++rb)
+    for (int m = 0; m < h->nd; ++m) {
+      ActLayer& A = h->acts[rb * 2 * h->nd + 2 * m + 1];
+      ConvLayer& c1 = h->c1[rb * h->nd + m];
+      ConvLayer& c2 = h->c2[rb * h->nd + m];
+      A.prescaled = false; c1.fold_out = nullptr; c2.fold_in = nullptr;
+      if (!enabled) continue;
+      host.resize(A.C);
+      CK(cudaMemcpyAsync(host.data(), A.alpha, (size_t)A.C * sizeof(float), cudaMemcpyDeviceToHost, s));
+      CK(cudaStreamSynchronize(s));
+      bool ok = true;
+      for (float a : host) ok = ok && a >= 1.f / 64.f && a <= 64.f;
+      if (!ok) continue;
+      if (!A.s2a) {
+        void* pv = nullptr;
+        if (dev_alloc(h, &pv, 2 * (size_t)A.C * sizeof(float))) return 1;
+        A.s2a = (float*)pv; A.inv_s2a = A.s2a + A.C;
+      }
+      std::vector<float> sc(2 * (size_t)A.C);
+      for (int c = 0; c < A.C; ++c) { sc[c] = 2.f * host[c]; sc[A.C + c] = 1.f / (2.f * host[c]); }
+      CK(cudaMemcpyAsync(A.s2a, sc.data(), sc.size() * sizeof(float), cudaMemcpyHostToDevice, s));
+      CK(cudaStreamSynchronize(s));
+      A.prescaled = true; c1.fold_out = A.s2a; c2.fold_in = A.inv_s2a;
+    }
+  return 0;
+}
+
 int bvg_finalize(bvg_handle* h, void* stream) {
   if (!h) return fail("bvg_finalize: null handle");
   cudaStream_t s = (cudaStream_t)stream;
   for (auto& kv : h->params)
     if (!kv.second.set) return fail("bvg_finalize: parameter '%s' was never set", kv.first.c_str());
+  for (auto& A : h->acts) if (finalize_act(h, A, s)) return 1;
+  if (finalize_act(h, h->act_post, s)) return 1;
+  if (fold_activation_scales(h, s)) return 1;
   if (finalize_conv(h, h->conv_pre, s, true)) return 1;
   for (auto& L : h->ups) if (finalize_conv(h, L, s, true)) return 1;
   for (auto& L : h->c1) if (finalize_conv(h, L, s, true)) return 1;
   for (auto& L : h->c2) if (finalize_conv(h, L, s, true)) return 1;
-  for (auto& A : h->acts) if (finalize_act(h, A, s)) return 1;
-  if (finalize_act(h, h->act_post, s)) return 1;
   // speaker encoder: all-or-nothing
   size_t nset = 0;
   for (auto& kv : h->ecapa_params) nset += kv.second.set ? 1 : 0;

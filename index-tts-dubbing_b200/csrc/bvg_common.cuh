@@ -66,6 +66,9 @@ struct ActArgs {
   const float* inv_beta;  // 1 / (exp(log_beta) + 1e-9)  [C]
   const SegDesc* seg;
   int R, C, B, max_len;
+  // 16-bit tensor-core kernel only: x holds 2*alpha*x_true per channel (folded into the producing convolution's weights)
+  // and y receives 2*alpha*y_true (unfolded by the consuming convolution's weights): saves the per-sample argument multiply
+  int prescaled;
 };
 
 // -------------------------------------------------------------------------------------------

@@ -928,7 +928,8 @@ __global__ void __launch_bounds__(FUSE ? NTHREADS_FUSED : 64 + 32 * EPW, 1) conv
 // fp32 [tap][Cin][N]  ->  bf16 images [ntile][kb][tap][chunk KC][n BN][8]
 template <typename T>
 __global__ void repack_umma_kernel(const float* __restrict__ wt, T* __restrict__ img, int ntaps, int Cin,
-                                   int N, int KC, int NKB, int BN, int NT) {
+                                   int N, int KC, int NKB, int BN, int NT, const float* __restrict__ out_scale,
+                                   const float* __restrict__ in_scale) {
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t total = (size_t)NT * NKB * ntaps * KC * BN * 8;
   if (idx >= total) return;
@@ -941,6 +942,10 @@ __global__ void repack_umma_kernel(const float* __restrict__ wt, T* __restrict__
   int nt = r / NKB;
   int ci = (kb * KC + c) * 8 + e, n = nt * BN + nn;
   float v = (ci < Cin && n < N) ? wt[((size_t)tap * Cin + ci) * N + n] : 0.f;
+  // per-channel scales folded into the image in fp32, before the one rounding to the storage type (plain Conv1d layers
+  // only: n is the output channel there)
+  if (out_scale && n < N) v *= out_scale[n];
+  if (in_scale && ci < Cin) v *= in_scale[ci];
   img[idx] = from_f32<T>(v);
 }
 
@@ -1099,9 +1104,10 @@ size_t umma_weight_image_bytes(int ntaps, int Cin, int N, bool small) {
 
 template <typename T>
 static void repack_umma_t(const float* wp_tap_major, T* img, const UmmaTiling& t, int ntaps, int Cin, int N, float acc_img_scale,
-                          cudaStream_t s) {
+                          const float* out_scale, const float* in_scale, cudaStream_t s) {
   size_t total = (size_t)t.NT * t.NKB * ntaps * t.KC * t.BN * 8;
-  repack_umma_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(wp_tap_major, img, ntaps, Cin, N, t.KC, t.NKB, t.BN, t.NT);
+  repack_umma_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(wp_tap_major, img, ntaps, Cin, N, t.KC, t.NKB, t.BN, t.NT,
+                                                                       out_scale, in_scale);
   if (has_identity(t, Cin, N)) {
     const size_t itotal = (size_t)t.NKB * t.KC * t.BN * 8;
     // set 0: I (residual), set 1: acc_img_scale * I (old output of an accumulating layer; exact for small integers)
@@ -1111,11 +1117,11 @@ static void repack_umma_t(const float* wp_tap_major, T* img, const UmmaTiling& t
 }
 
 cudaError_t launch_repack_umma(const float* wp_tap_major, void* img, int dtype, int ntaps, int Cin, int N, float acc_img_scale,
-                               bool small, cudaStream_t s) {
+                               bool small, cudaStream_t s, const float* out_scale, const float* in_scale) {
   UmmaTiling t = make_tiling(ntaps, Cin, N, small);
   if (!t.ok || (dtype != 1 && dtype != 2)) return cudaErrorInvalidValue;
-  if (dtype == 1) repack_umma_t(wp_tap_major, (__nv_bfloat16*)img, t, ntaps, Cin, N, acc_img_scale, s);
-  else repack_umma_t(wp_tap_major, (__half*)img, t, ntaps, Cin, N, acc_img_scale, s);
+  if (dtype == 1) repack_umma_t(wp_tap_major, (__nv_bfloat16*)img, t, ntaps, Cin, N, acc_img_scale, out_scale, in_scale, s);
+  else repack_umma_t(wp_tap_major, (__half*)img, t, ntaps, Cin, N, acc_img_scale, out_scale, in_scale, s);
   return cudaGetLastError();
 }
 

@@ -175,9 +175,19 @@ __global__ void zero_guards_all_kernel(const GuardJobs jobs, int B) {
   for (int i = threadIdx.x; i < n; i += blockDim.x) p[i] = z;
 }
 
+__global__ void scale_vec_kernel(const float* __restrict__ x, const float* __restrict__ sc, float* __restrict__ y, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = x[i] * sc[i];
+}
+
 inline int nblk(size_t n, int t) { return (int)((n + t - 1) / t); }
 
 }  // namespace
+
+cudaError_t launch_scale_vec(const float* x, const float* scale, float* y, int n, cudaStream_t s) {
+  scale_vec_kernel<<<nblk(n, 256), 256, 0, s>>>(x, scale, y, n);
+  return cudaGetLastError();
+}
 
 bool bvg_pdl_enabled() {
   static const bool on = [] { const char* e = getenv("BVG_PDL"); return e ? atoi(e) != 0 : true; }();
