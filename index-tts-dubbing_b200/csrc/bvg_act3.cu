@@ -283,13 +283,18 @@ act1d_c8_mma_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __r
       v[0] = fmaf(-hh[0], __cosf(a2[0] * c[0]), c[0]); v[1] = fmaf(-hh[0], __cosf(a2[0] * c[1]), c[1]);
       v[2] = fmaf(-hh[1], __cosf(a2[1] * c[2]), c[2]); v[3] = fmaf(-hh[1], __cosf(a2[1] * c[3]), c[3]);
     };
+    // the accumulator's initial value (h per channel row) as four registers the compiler treats as distinct values, so
+    // that it keeps the aligned quad alive instead of rebuilding it with moves in every step
+    float hq[4];
+    asm volatile("mov.f32 %0, %4; mov.f32 %1, %4; mov.f32 %2, %5; mov.f32 %3, %5;"
+                 : "=f"(hq[0]), "=f"(hq[1]), "=f"(hq[2]), "=f"(hq[3]) : "f"(hh[0]), "f"(hh[1]));
     auto down = [&](int J, const uint32_t (&C)[4], const uint32_t (&N)[4]) {
       float c[4];
       if (BVG_ACT_EXP & 2) {
         c[0] = __uint_as_float(C[0] ^ N[0]); c[1] = __uint_as_float(C[1] ^ N[1]);
         c[2] = __uint_as_float(C[2] ^ N[2]); c[3] = __uint_as_float(C[3] ^ N[3]);
       } else {
-        mma16816<__half>(c, C, fdn[0][0], fdn[0][1], hh[0], hh[0], hh[1], hh[1]);
+        mma16816<__half>(c, C, fdn[0][0], fdn[0][1], hq[0], hq[1], hq[2], hq[3]);
         mma16816<__half>(c, N, fdn[1][0], fdn[1][1], c[0], c[1], c[2], c[3]);
       }
       // the raw rows these outputs overwrite (region rows 8J+8 .. 8J+15) were consumed by column tiles <= 2J+2; later

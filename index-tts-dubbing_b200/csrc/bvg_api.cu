@@ -58,6 +58,8 @@ struct ConvLayer {
   const float* fold_out = nullptr;   // [Cout]
   const float* fold_in = nullptr;    // [Cin]
   float* bias_umma = nullptr;        // bias * fold_out (used instead of `bias` by the tcgen05 path)
+  const float* fold_res = nullptr;   // [Cout] factor on the residual input (the residual stream is stored pre-scaled)
+  float* fold_buf = nullptr;         // device storage owned by this layer for fold_out / fold_res products ([2 * Cout])
   void setup() {
     if (!transposed) {
       ntaps = k; N = Cout; u = 1; p = 0; q_extra = 0;
@@ -73,7 +75,6 @@ struct ConvLayer {
 struct ActLayer {
   int C = 0;
   float *la = nullptr, *lb = nullptr, *alpha = nullptr, *inv_beta = nullptr;
-  float *s2a = nullptr, *inv_s2a = nullptr;   // 2 alpha and its reciprocal (device, [C]) when the layer is pre-scaled
   bool prescaled = false;   // 16-bit modes: input / output carry the factor 2 alpha, folded into the neighbouring convolutions
 };
 
@@ -222,6 +223,7 @@ ConvArgs make_conv_args(const ConvLayer& L, const bvg_plan* p, int gin, int gout
                         bool umma, const ActLayer* act = nullptr) {
   ConvArgs a{};
   a.x = x; a.y = y; a.res = res;
+  a.res_scale = (umma && res) ? L.fold_res : nullptr;
   a.dtype = p->dtype;
   a.w = umma ? (const void*)(p->dtype == 2 ? L.w_umma16 : L.w_umma) : (const void*)L.w_tap;
   if (umma && L.w_umma_s && !act) {
@@ -482,8 +484,8 @@ static int finalize_conv(bvg_handle* h, ConvLayer& L, cudaStream_t s, bool want_
       if (!L.w_umma16) {
         if (dev_alloc(h, &L.w_umma16, bytes)) return 1;
       }
-      CK(launch_repack_umma(L.w_tap, L.w_umma, 1, L.ntaps, L.Cin, L.N, (float)h->nk, false, s, L.fold_out, L.fold_in));
-      CK(launch_repack_umma(L.w_tap, L.w_umma16, 2, L.ntaps, L.Cin, L.N, (float)h->nk, false, s, L.fold_out, L.fold_in));
+      CK(launch_repack_umma(L.w_tap, L.w_umma, 1, L.ntaps, L.Cin, L.N, (float)h->nk, false, s, L.fold_out, L.fold_in, L.fold_res));
+      CK(launch_repack_umma(L.w_tap, L.w_umma16, 2, L.ntaps, L.Cin, L.N, (float)h->nk, false, s, L.fold_out, L.fold_in, L.fold_res));
       if (L.fold_out) {
         if (!L.bias_umma) {
           void* pb = nullptr;
@@ -495,8 +497,8 @@ static int finalize_conv(bvg_handle* h, ConvLayer& L, cudaStream_t s, bool want_
       const size_t sbytes = L.N >= 256 ? umma_weight_image_bytes(L.ntaps, L.Cin, L.N, true) : 0;
       if (sbytes) {
         if (!L.w_umma_s && (dev_alloc(h, &L.w_umma_s, sbytes) || dev_alloc(h, &L.w_umma16_s, sbytes))) return 1;
-        CK(launch_repack_umma(L.w_tap, L.w_umma_s, 1, L.ntaps, L.Cin, L.N, (float)h->nk, true, s, L.fold_out, L.fold_in));
-        CK(launch_repack_umma(L.w_tap, L.w_umma16_s, 2, L.ntaps, L.Cin, L.N, (float)h->nk, true, s, L.fold_out, L.fold_in));
+        CK(launch_repack_umma(L.w_tap, L.w_umma_s, 1, L.ntaps, L.Cin, L.N, (float)h->nk, true, s, L.fold_out, L.fold_in, L.fold_res));
+        CK(launch_repack_umma(L.w_tap, L.w_umma16_s, 2, L.ntaps, L.Cin, L.N, (float)h->nk, true, s, L.fold_out, L.fold_in, L.fold_res));
       }
     }
   }
@@ -514,44 +516,98 @@ static int finalize_act(bvg_handle* h, ActLayer& A, cudaStream_t s) {
   return 0;
 }
 
-// 16-bit modes: the SECOND activation of every AMPBlock1 step (models.py:69-72: xt = c1(act1(x)); xt = c2(act2(xt))) reads a
-// tensor only it consumes (c1's output) and writes one only c2 consumes.  Folding 2 alpha per channel into c1's output
-// channels (weights and bias) and 1 / (2 alpha) into c2's input channels lets that activation run "pre-scaled": the up-FIR
-// delivers the cosine's argument directly, one multiply per activated sample less (bvg_act3.cu, PRE).  The fold happens in
-// fp32 before the images are rounded; a layer whose alpha leaves [1/64, 64] keeps the plain kernel (fp16 range).  The fp32
-// parity mode, the per-op entry points and the experimental fused kernel use the unfolded parameters.
+// 16-bit modes: pre-scaled activations.  An AMPBlock1 (models.py:65-74) runs, for m = 0 .. nd-1,
+//     x_{m+1} = c2_m(act2_m(c1_m(act1_m(x_m)))) + x_m.
+// The tensor-core activation kernel has a variant (bvg_act3.cu, PRE) whose input already carries the factor 2 alpha per
+// channel -- the up-FIR then delivers the cosine's argument directly, one multiply per activated sample less -- and whose
+// output keeps that factor.  All the factors are folded into the neighbouring convolutions here, in fp32, before the UMMA
+// images are rounded once:
+//   * act2_m: reads only c1_m's output, feeds only c2_m  ->  2 alpha into c1_m's output channels (weights and bias),
+//     1 / (2 alpha) into c2_m's input channels;
+//   * act1_m, m >= 1: reads the residual stream x_m, which c2_{m-1} writes and c2_m adds back  ->  x_m is STORED as
+//     s_m x_m (s_m = 2 alpha of act1_m): s_m into c2_{m-1}'s output channels and bias, 1 / s_m into c1_m's input channels,
+//     and a per-channel factor on each c2's residual input (s_{m+1} / s_m, with s = 1 where nothing is folded: x_0 is the
+//     stage input shared by the nk resblocks, and the last c2 accumulates into the unscaled stage output) -- the diagonal of
+//     the residual identity image for the narrow layers, a multiply in the epilogue for the wide ones.
+// A layer whose alpha leaves [1/64, 64] keeps the plain kernel (fp16 range).  The fp32 parity mode, the per-op entry points
+// and the experimental fused kernel use the unfolded parameters.
 static int fold_activation_scales(bvg_handle* h, cudaStream_t s) {
   static const int enabled = [] {
-    const char* e = getenv("BVG_ACT_FOLD");
+    const char* e = getenv("BVG_ACT_FOLD");   // 0 = off, 1 = act2 only, 2 (default) = act2 and the act1 of m >= 1
     const char* f = getenv("BVG_FUSE_ACT");   // the experimental fused kernel and the register-streamed kernel
     const char* m = getenv("BVG_ACT_MMA");    // (BVG_ACT_MMA=0) have no pre-scaled variant
-    return (e ? atoi(e) != 0 : true) && !(f && atoi(f)) && !(m && !atoi(m));
+    if ((f && atoi(f)) || (m && !atoi(m))) return 0;
+    return e ? atoi(e) : 2;
   }();
-  std::vector<float> host;
-  for (size_t rb = 0; rb < (size_t)h->nups * h->nk; ++rb)
-    for (int m = 0; m < h->nd; ++m) {
-      ActLayer& A = h->acts[rb * 2 * h->nd + 2 * m + 1];
-      ConvLayer& c1 = h->c1[rb * h->nd + m];
-      ConvLayer& c2 = h->c2[rb * h->nd + m];
-      A.prescaled = false; c1.fold_out = nullptr; c2.fold_in = nullptr;
-      if (!enabled) continue;
-      host.resize(A.C);
-      CK(cudaMemcpyAsync(host.data(), A.alpha, (size_t)A.C * sizeof(float), cudaMemcpyDeviceToHost, s));
-      CK(cudaStreamSynchronize(s));
-      bool ok = true;
-      for (float a : host) ok = ok && a >= 1.f / 64.f && a <= 64.f;
-      if (!ok) continue;
-      if (!A.s2a) {
-        void* pv = nullptr;
-        if (dev_alloc(h, &pv, 2 * (size_t)A.C * sizeof(float))) return 1;
-        A.s2a = (float*)pv; A.inv_s2a = A.s2a + A.C;
-      }
-      std::vector<float> sc(2 * (size_t)A.C);
-      for (int c = 0; c < A.C; ++c) { sc[c] = 2.f * host[c]; sc[A.C + c] = 1.f / (2.f * host[c]); }
-      CK(cudaMemcpyAsync(A.s2a, sc.data(), sc.size() * sizeof(float), cudaMemcpyHostToDevice, s));
-      CK(cudaStreamSynchronize(s));
-      A.prescaled = true; c1.fold_out = A.s2a; c2.fold_in = A.inv_s2a;
+  const int nd = h->nd;
+  auto alpha_host = [&](const ActLayer& A, std::vector<float>& out) -> int {
+    out.resize(A.C);
+    CK(cudaMemcpyAsync(out.data(), A.alpha, (size_t)A.C * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return 0;
+  };
+  auto in_range = [](const std::vector<float>& a) {
+    bool ok = true;
+    for (float v : a) ok = ok && v >= 1.f / 64.f && v <= 64.f;
+    return ok;
+  };
+  auto upload = [&](float** dst, size_t n, const std::vector<float>& v) -> int {
+    if (!*dst) {
+      void* pv = nullptr;
+      if (dev_alloc(h, &pv, n * sizeof(float))) return 1;
+      *dst = (float*)pv;
     }
+    CK(cudaMemcpyAsync(*dst, v.data(), n * sizeof(float), cudaMemcpyHostToDevice, s));
+    CK(cudaStreamSynchronize(s));
+    return 0;
+  };
+  for (size_t rb = 0; rb < (size_t)h->nups * h->nk; ++rb) {
+    const int C = h->c1[rb * nd].Cin;
+    // host copies of 2 alpha for the 2 nd activations of this resblock (empty = not pre-scaled)
+    std::vector<std::vector<float>> sc(2 * nd);
+    for (int a = 0; a < 2 * nd; ++a) {
+      ActLayer& A = h->acts[rb * 2 * nd + a];
+      A.prescaled = false;
+      const bool is_act2 = a & 1;
+      const bool want = enabled >= 1 && (is_act2 || (enabled >= 2 && a >= 2));   // act1 of m = 0 reads the shared stage input
+      if (!want) continue;
+      std::vector<float> al;
+      if (alpha_host(A, al)) return 1;
+      if (!in_range(al)) continue;
+      for (float& v : al) v *= 2.f;
+      sc[a] = al;
+      A.prescaled = true;
+    }
+    for (int m = 0; m < nd; ++m) {
+      ConvLayer& c1 = h->c1[rb * nd + m];
+      ConvLayer& c2 = h->c2[rb * nd + m];
+      const std::vector<float>& s1 = sc[2 * m];                                  // act1_m: scale of the stored x_m
+      const std::vector<float>& s2 = sc[2 * m + 1];                              // act2_m
+      static const std::vector<float> none;
+      const std::vector<float>& snext = m + 1 < nd ? sc[2 * (m + 1)] : none;     // scale of the stored x_{m+1}
+      // c1_m: input channels / s1, output channels * s2          c2_m: input / s2, output * snext, residual * snext / s1
+      std::vector<float> buf(2 * (size_t)C);
+      c1.fold_in = c1.fold_out = c2.fold_in = c2.fold_out = c2.fold_res = nullptr; c1.fold_res = nullptr;
+      if (!s1.empty() || !s2.empty()) {
+        for (int c = 0; c < C; ++c) { buf[c] = s1.empty() ? 1.f : 1.f / s1[c]; buf[C + c] = s2.empty() ? 1.f : s2[c]; }
+        if (upload(&c1.fold_buf, buf.size(), buf)) return 1;
+        if (!s1.empty()) c1.fold_in = c1.fold_buf;
+        if (!s2.empty()) c1.fold_out = c1.fold_buf + C;
+      }
+      if (!s2.empty() || !snext.empty() || !s1.empty()) {
+        std::vector<float> b3(3 * (size_t)C);
+        for (int c = 0; c < C; ++c) {
+          b3[c] = s2.empty() ? 1.f : 1.f / s2[c];
+          b3[C + c] = snext.empty() ? 1.f : snext[c];
+          b3[2 * C + c] = (snext.empty() ? 1.f : snext[c]) / (s1.empty() ? 1.f : s1[c]);
+        }
+        if (upload(&c2.fold_buf, b3.size(), b3)) return 1;
+        if (!s2.empty()) c2.fold_in = c2.fold_buf;
+        if (!snext.empty()) c2.fold_out = c2.fold_buf + C;
+        if (!snext.empty() || !s1.empty()) c2.fold_res = c2.fold_buf + 2 * C;
+      }
+    }
+  }
   return 0;
 }
 

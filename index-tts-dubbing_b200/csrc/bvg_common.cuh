@@ -31,6 +31,7 @@ struct ConvArgs {
   const void* x;        // [Cin/8][Rx][8]
   void* y;              // [Cout/8][Ry][8]
   const void* res;      // residual, geometry of y, or nullptr
+  const float* res_scale;   // optional per-output-channel factor on the residual (tcgen05 kernel; nullptr = 1)
   const void* w;        // kernel-specific weight image
   const float* bias;    // bias[b * bias_bstride + co]
   const SegDesc* seg_in;

@@ -209,6 +209,13 @@ __device__ __forceinline__ void unpack_add(const uint4& p, float (&v)[8]) {
   }
 }
 template <bool F16>
+__device__ __forceinline__ void unpack_fma(const uint4& p, float (&v)[8], const float4& s0, const float4& s1) {
+  float r[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  unpack_add<F16>(p, r);
+  v[0] = fmaf(r[0], s0.x, v[0]); v[1] = fmaf(r[1], s0.y, v[1]); v[2] = fmaf(r[2], s0.z, v[2]); v[3] = fmaf(r[3], s0.w, v[3]);
+  v[4] = fmaf(r[4], s1.x, v[4]); v[5] = fmaf(r[5], s1.y, v[5]); v[6] = fmaf(r[6], s1.z, v[6]); v[7] = fmaf(r[7], s1.w, v[7]);
+}
+template <bool F16>
 __device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
   uint4 o;
   if constexpr (F16) {
@@ -717,6 +724,13 @@ __global__ void __launch_bounds__(FUSE ? NTHREADS_FUSED : 64 + 32 * EPW, 1) conv
 #pragma unroll
             for (int j = 0; j < 8; ++j) bv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
           }
+          float4 rsc[8];   // per-channel residual factors (pre-scaled residual stream, see fold_activation_scales)
+          const bool rscaled = rg != nullptr && a.res_scale != nullptr;
+          if (rscaled) {
+            const float4* g4 = reinterpret_cast<const float4*>(a.res_scale + nbase);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) rsc[j] = nbase + 4 * j < N ? __ldg(g4 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
           uint4 resv[4], oldv[4];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
@@ -731,7 +745,10 @@ __global__ void __launch_bounds__(FUSE ? NTHREADS_FUSED : 64 + 32 * EPW, 1) conv
             v[2] = __uint_as_float(r[8 * u + 2]) + bv[2 * u].z; v[3] = __uint_as_float(r[8 * u + 3]) + bv[2 * u].w;
             v[4] = __uint_as_float(r[8 * u + 4]) + bv[2 * u + 1].x; v[5] = __uint_as_float(r[8 * u + 5]) + bv[2 * u + 1].y;
             v[6] = __uint_as_float(r[8 * u + 6]) + bv[2 * u + 1].z; v[7] = __uint_as_float(r[8 * u + 7]) + bv[2 * u + 1].w;
-            if (rg && ok[u]) unpack_add<F16>(resv[u], v);
+            if (rg && ok[u]) {
+              if (rscaled) unpack_fma<F16>(resv[u], v, rsc[2 * u], rsc[2 * u + 1]);
+              else unpack_add<F16>(resv[u], v);
+            }
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[j] *= a.out_scale;
             if (accum_epi && ok[u]) unpack_add<F16>(oldv[u], v);
@@ -951,7 +968,8 @@ __global__ void repack_umma_kernel(const float* __restrict__ wt, T* __restrict__
 
 // identity images [kb][chunk KC][n BN][8] appended after the conv images of a square (Cin == N), single-n-tile layer
 template <typename T>
-__global__ void identity_umma_kernel(T* __restrict__ img, int N, int KC, int NKB, int BN, float value) {
+__global__ void identity_umma_kernel(T* __restrict__ img, int N, int KC, int NKB, int BN, float value,
+                                     const float* __restrict__ diag /* optional per-channel factor */) {
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t total = (size_t)NKB * KC * BN * 8;
   if (idx >= total) return;
@@ -961,7 +979,7 @@ __global__ void identity_umma_kernel(T* __restrict__ img, int N, int KC, int NKB
   int c = r % KC;
   int kb = r / KC;
   int ci = (kb * KC + c) * 8 + e;
-  img[idx] = from_f32<T>((ci == nn && nn < N) ? value : 0.f);
+  img[idx] = from_f32<T>((ci == nn && nn < N) ? (diag ? value * diag[nn] : value) : 0.f);
 }
 
 bool has_identity(const UmmaTiling& t, int Cin, int N) { return t.ok && t.NT == 1 && Cin == N; }
@@ -1104,24 +1122,24 @@ size_t umma_weight_image_bytes(int ntaps, int Cin, int N, bool small) {
 
 template <typename T>
 static void repack_umma_t(const float* wp_tap_major, T* img, const UmmaTiling& t, int ntaps, int Cin, int N, float acc_img_scale,
-                          const float* out_scale, const float* in_scale, cudaStream_t s) {
+                          const float* out_scale, const float* in_scale, const float* res_diag, cudaStream_t s) {
   size_t total = (size_t)t.NT * t.NKB * ntaps * t.KC * t.BN * 8;
   repack_umma_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(wp_tap_major, img, ntaps, Cin, N, t.KC, t.NKB, t.BN, t.NT,
                                                                        out_scale, in_scale);
   if (has_identity(t, Cin, N)) {
     const size_t itotal = (size_t)t.NKB * t.KC * t.BN * 8;
     // set 0: I (residual), set 1: acc_img_scale * I (old output of an accumulating layer; exact for small integers)
-    identity_umma_kernel<T><<<(unsigned)((itotal + 255) / 256), 256, 0, s>>>(img + total, N, t.KC, t.NKB, t.BN, 1.f);
-    identity_umma_kernel<T><<<(unsigned)((itotal + 255) / 256), 256, 0, s>>>(img + total + itotal, N, t.KC, t.NKB, t.BN, acc_img_scale);
+    identity_umma_kernel<T><<<(unsigned)((itotal + 255) / 256), 256, 0, s>>>(img + total, N, t.KC, t.NKB, t.BN, 1.f, res_diag);
+    identity_umma_kernel<T><<<(unsigned)((itotal + 255) / 256), 256, 0, s>>>(img + total + itotal, N, t.KC, t.NKB, t.BN, acc_img_scale, nullptr);
   }
 }
 
 cudaError_t launch_repack_umma(const float* wp_tap_major, void* img, int dtype, int ntaps, int Cin, int N, float acc_img_scale,
-                               bool small, cudaStream_t s, const float* out_scale, const float* in_scale) {
+                               bool small, cudaStream_t s, const float* out_scale, const float* in_scale, const float* res_diag) {
   UmmaTiling t = make_tiling(ntaps, Cin, N, small);
   if (!t.ok || (dtype != 1 && dtype != 2)) return cudaErrorInvalidValue;
-  if (dtype == 1) repack_umma_t(wp_tap_major, (__nv_bfloat16*)img, t, ntaps, Cin, N, acc_img_scale, out_scale, in_scale, s);
-  else repack_umma_t(wp_tap_major, (__half*)img, t, ntaps, Cin, N, acc_img_scale, out_scale, in_scale, s);
+  if (dtype == 1) repack_umma_t(wp_tap_major, (__nv_bfloat16*)img, t, ntaps, Cin, N, acc_img_scale, out_scale, in_scale, res_diag, s);
+  else repack_umma_t(wp_tap_major, (__half*)img, t, ntaps, Cin, N, acc_img_scale, out_scale, in_scale, res_diag, s);
   return cudaGetLastError();
 }
 
