@@ -60,6 +60,7 @@ struct ConvLayer {
   float* bias_umma = nullptr;        // bias * fold_out (used instead of `bias` by the tcgen05 path)
   const float* fold_res = nullptr;   // [Cout] factor on the residual input (the residual stream is stored pre-scaled)
   float* fold_buf = nullptr;         // device storage owned by this layer for fold_out / fold_res products ([2 * Cout])
+  bool k_packed = false;             // the UMMA images are K-packed (24-channel layers, bvg_conv_umma.cu)
   void setup() {
     if (!transposed) {
       ntaps = k; N = Cout; u = 1; p = 0; q_extra = 0;
@@ -224,6 +225,7 @@ ConvArgs make_conv_args(const ConvLayer& L, const bvg_plan* p, int gin, int gout
   ConvArgs a{};
   a.x = x; a.y = y; a.res = res;
   a.res_scale = (umma && res) ? L.fold_res : nullptr;
+  a.k_packed = (umma && L.k_packed) ? 1 : 0;
   a.dtype = p->dtype;
   a.w = umma ? (const void*)(p->dtype == 2 ? L.w_umma16 : L.w_umma) : (const void*)L.w_tap;
   if (umma && L.w_umma_s && !act) {
@@ -476,7 +478,8 @@ static int finalize_conv(bvg_handle* h, ConvLayer& L, cudaStream_t s, bool want_
   if (L.transposed) CK(launch_repack_convt(L.w_raw, L.w_tap, L.Cin, L.Cout, L.k, L.u, s));
   else CK(launch_repack_conv(L.w_raw, L.w_tap, L.Cout, L.Cin, L.k, s));
   if (want_umma) {
-    size_t bytes = umma_weight_image_bytes(L.ntaps, L.Cin, L.N);
+    L.k_packed = !L.transposed && umma_k_packed_default(L.Cin, L.N);
+    size_t bytes = umma_weight_image_bytes(L.ntaps, L.Cin, L.N, false, L.k_packed);
     if (bytes) {
       if (!L.w_umma) {
         if (dev_alloc(h, &L.w_umma, bytes)) return 1;
@@ -484,8 +487,8 @@ static int finalize_conv(bvg_handle* h, ConvLayer& L, cudaStream_t s, bool want_
       if (!L.w_umma16) {
         if (dev_alloc(h, &L.w_umma16, bytes)) return 1;
       }
-      CK(launch_repack_umma(L.w_tap, L.w_umma, 1, L.ntaps, L.Cin, L.N, (float)h->nk, false, s, L.fold_out, L.fold_in, L.fold_res));
-      CK(launch_repack_umma(L.w_tap, L.w_umma16, 2, L.ntaps, L.Cin, L.N, (float)h->nk, false, s, L.fold_out, L.fold_in, L.fold_res));
+      CK(launch_repack_umma(L.w_tap, L.w_umma, 1, L.ntaps, L.Cin, L.N, (float)h->nk, false, s, L.fold_out, L.fold_in, L.fold_res, L.k_packed));
+      CK(launch_repack_umma(L.w_tap, L.w_umma16, 2, L.ntaps, L.Cin, L.N, (float)h->nk, false, s, L.fold_out, L.fold_in, L.fold_res, L.k_packed));
       if (L.fold_out) {
         if (!L.bias_umma) {
           void* pb = nullptr;
@@ -1021,6 +1024,7 @@ int conv_op(bool transposed, const float* x, const float* w, const float* bias, 
     }
   }
   if (mode != BVG_MODE_FP32) {
+    if (!a.act_alpha && !transposed && umma_k_packed_default(Cin, L.N)) a.k_packed = 1;   // as bvg_forward does (not with the fused kernel)
     if (!a.act_alpha && L.N >= 256) {   // same rule as bvg_forward: the small-batch variant when few CTAs would run
       int dev = 0, sms = 148;
       cudaGetDevice(&dev);
@@ -1037,10 +1041,10 @@ int conv_op(bool transposed, const float* x, const float* w, const float* bias, 
     CK(cudaMemcpyAsync(pf_dev, pf.data(), pf.size() * sizeof(int), cudaMemcpyHostToDevice, s));
     CK(cudaStreamSynchronize(s));
     a.tile_prefix = pf_dev; a.total_mt = pf[B];
-    size_t bytes = umma_weight_image_bytes(L.ntaps, Cin, L.N, a.bn_small != 0);
+    size_t bytes = umma_weight_image_bytes(L.ntaps, Cin, L.N, a.bn_small != 0, a.k_packed != 0);
     if (!bytes || !conv_umma_supported(a)) return fail("conv op: shape not supported by the tcgen05 kernel");
     if (tmp.alloc(&wu, bytes)) return 1;
-    CK(launch_repack_umma(wt, wu, dt, L.ntaps, Cin, L.N, 1.f, a.bn_small != 0, s));
+    CK(launch_repack_umma(wt, wu, dt, L.ntaps, Cin, L.N, 1.f, a.bn_small != 0, s, nullptr, nullptr, nullptr, a.k_packed != 0));
     a.w = wu;
     CK(launch_conv_umma(a, s));
   } else {

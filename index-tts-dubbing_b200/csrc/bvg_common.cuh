@@ -54,6 +54,7 @@ struct ConvArgs {
   int total_mt;             // tile_prefix[B]
   int msub;                 // 1, 2 or 4
   int bn_small;             // 1: `w` is the 64-column n-tile image (small-batch variant of a wide layer), msub must be 1
+  int k_packed;             // 1: `w` is the K-packed image of a 24-channel layer (taps share K-steps, see make_tiling)
   // fused Activation1d (tcgen05 kernel, bf16): when set, x is the RAW input and the kernel applies the
   // activation with these per-input-channel parameters while staging its A operand
   const float* act_alpha;

@@ -73,6 +73,10 @@ struct UmmaTiling {
   int KC, NKB;      // 8-channel chunks per k-block, k-blocks
   int BN, NT;       // columns per CTA tile (multiple of 16, <= 256), n tiles
   int BNC;          // TMEM columns per accumulator (BN rounded up to 32)
+  // K-packed mode (Cin = 24): a tap holds 3 real 8-channel chunks, i.e. 1.5 K-steps; instead of padding every tap to 2
+  // K-steps with a zero chunk, the (tap, chunk) items are laid out back to back: K-step s multiplies items 2s and 2s+1,
+  // which may belong to different taps (the A descriptor's start address and K-chunk stride are per K-step then).
+  int packed, nks, nstg;   // nstg: weight stages per k-block (= ntaps when not packed; a stage = KC chunks = KC/2 K-steps)
   bool ok;
 };
 
@@ -85,9 +89,10 @@ inline int env_int(const char* name, int dflt) {
 // Tiling that only depends on the layer (the weight image layout depends on it).  `small`: 64-column n-tiles -- the
 // small-batch variant of the wide layers: with only a few m-tiles (one short utterance) a 256-column n-tile leaves
 // 3-12 CTAs streaming 4-13 MB of weights each; four times as many CTAs stream a quarter each.
-inline UmmaTiling make_tiling(int ntaps, int Cin, int N, bool small = false) {
+inline UmmaTiling make_tiling(int ntaps, int Cin, int N, bool small = false, bool packed = false) {
   UmmaTiling t{};
   t.ok = false;
+  t.packed = 0; t.nks = 0; t.nstg = ntaps;
   if (Cin % 8 || N % 8 || ntaps < 1 || ntaps > BVG_MAX_TAPS) return t;
   const int cin_pad = round_up_i(Cin, 16);
   if (cin_pad % 64 == 0) { t.KC = 8; t.NKB = cin_pad / 64; }
@@ -101,6 +106,12 @@ inline UmmaTiling make_tiling(int ntaps, int Cin, int N, bool small = false) {
   t.NT = (n_pad + bnmax - 1) / bnmax;
   t.BN = round_up_i((n_pad + t.NT - 1) / t.NT, 16);
   t.BNC = round_up_i(t.BN, 32);
+  if (packed) {
+    if (Cin != 24 || t.NT != 1) return t;   // only the 24-channel layers (KC = 4: three real chunks + one zero chunk)
+    t.packed = 1;
+    t.nks = (3 * ntaps + 1) / 2;
+    t.nstg = (t.nks + 1) / 2;
+  }
   t.ok = true;
   return t;
 }
@@ -311,6 +322,7 @@ struct UmmaKernelArgs {
   // same trick for `accumulate` (y = old + ...): the old output tile x (1/out_scale) * identity (second image set)
   int acc_mma;
   int n_extra;              // res_mma + acc_mma: extra k-block groups after the convolution's
+  int packed, nks, nstg;    // K-packed mode (see UmmaTiling); nstg = weight stages of the convolution part per k-block
   unsigned long long* trace;   // optional event trace of CTA 0 (BVG_CONV_TRACE), nullptr normally
   int debug;                // tuning aid (BVG_CONV_DEBUG): 1 = epilogue skips global memory, 2 = no MMAs, 4 = no A loads
 };
@@ -355,7 +367,7 @@ __global__ void __launch_bounds__(FUSE ? NTHREADS_FUSED : 64 + 32 * EPW, 1) conv
   }
   // batch-independent bias (the AMP-block convolutions): staged once in shared memory, zero padded to
   // whole 32-column groups, so the epilogue reads it with broadcast LDS instead of dependent L1 loads
-  float* sbias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 20) + 15) & ~(uintptr_t)15);
+  float* sbias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 28) + 15) & ~(uintptr_t)15);   // [2..27]: the issuer's tap / K-step table
   const bool use_sbias = a.bias != nullptr && a.bias_bstride == 0 && ka.NT * ka.BN <= SBIAS_MAX;
   if (use_sbias) {
     const int N_ = a.u * a.Cout;
@@ -478,10 +490,10 @@ __global__ void __launch_bounds__(FUSE ? NTHREADS_FUSED : 64 + 32 * EPW, 1) conv
           if (++sa == ka.NA) { sa = 0; pa ^= 1; }
           }
           if (!ka.b_resident || first) {
-            for (int tap = 0; tap < a.ntaps; ++tap) {
+            for (int tap = 0; tap < ka.nstg; ++tap) {
               if (!ka.b_resident) mbar_wait(B_EMPTY(sb), pb ^ 1);
               mbar_expect_tx(B_FULL(sb), (uint32_t)ka.b_stage_bytes);
-              const uint8_t* src = wimg + ((size_t)(nt * ka.NKB + kb) * a.ntaps + tap) * ka.b_stage_bytes;
+              const uint8_t* src = wimg + ((size_t)(nt * ka.NKB + kb) * ka.nstg + tap) * ka.b_stage_bytes;
               bulk_g2s(smem_u32(b_smem + (size_t)sb * ka.b_stage_bytes), src, (uint32_t)ka.b_stage_bytes, B_FULL(sb));
               if (++sb == ka.NB) { sb = 0; pb ^= 1; }
             }
@@ -505,7 +517,7 @@ __global__ void __launch_bounds__(FUSE ? NTHREADS_FUSED : 64 + 32 * EPW, 1) conv
             if (!ka.b_resident || first) {
               if (!ka.b_resident) mbar_wait(B_EMPTY(sb), pb ^ 1);
               mbar_expect_tx(B_FULL(sb), (uint32_t)ka.b_stage_bytes);
-              const uint8_t* src = wimg + ((size_t)ka.NKB * (a.ntaps + img_set) + kb) * ka.b_stage_bytes;   // identity images (NT == 1)
+              const uint8_t* src = wimg + ((size_t)ka.NKB * (ka.nstg + img_set) + kb) * ka.b_stage_bytes;   // identity images (NT == 1)
               bulk_g2s(smem_u32(b_smem + (size_t)sb * ka.b_stage_bytes), src, (uint32_t)ka.b_stage_bytes, B_FULL(sb));
               if (++sb == ka.NB) { sb = 0; pb ^= 1; }
             }
@@ -528,9 +540,10 @@ __global__ void __launch_bounds__(FUSE ? NTHREADS_FUSED : 64 + 32 * EPW, 1) conv
       uint32_t* tapshift = reinterpret_cast<uint32_t*>(tmem_slot + 2);   // [ntaps + 1] row shifts (16-byte units)
       for (int tp = 0; tp < a.ntaps; ++tp) tapshift[tp] = (uint32_t)(a.tap_off[tp] - ka.minoff);
       tapshift[a.ntaps] = 0;
-      auto run = [&](auto ms_tag, auto nk_tag) {
+      auto run = [&](auto ms_tag, auto nk_tag, auto pk_tag) {
         constexpr int MS = decltype(ms_tag)::value;
         constexpr int NK = decltype(nk_tag)::value;   // K-steps per tap known at compile time (0 = runtime loop)
+        constexpr bool PK = decltype(pk_tag)::value;  // K-packed 24-channel layer (NK == 2)
         // instruction descriptor: D=f32, A=B=bf16 (format 1) or fp16 (format 0), both K-major, N=BN, M=128
         const uint32_t idesc = (1u << 4) | (F16 ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)(ka.BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         const uint32_t lbo_a = (uint32_t)ka.astride * 16, lbo_b = (uint32_t)ka.BN * 16;
@@ -544,6 +557,7 @@ __global__ void __launch_bounds__(FUSE ? NTHREADS_FUSED : 64 + 32 * EPW, 1) conv
         const uint32_t a_stage_lo = (uint32_t)ka.a_stage_bytes >> 4, b_stage_lo = (uint32_t)ka.b_stage_bytes >> 4;
         const uint32_t bnc = (uint32_t)ka.BNC;
         const uint32_t res_shift = (uint32_t)(-ka.minoff);
+        const uint32_t a_lbo_word = (uint32_t)adesc0;   // the K-chunk stride field of the low word (K-packed steps carry their own)
         const int ntaps = a.ntaps, NKB = ka.NKB, NA = ka.NA, NB = ka.NB, NACC = ka.ACC;
         const bool resident = ka.b_resident != 0;
         int sa = 0, pa = 0, sb = 0, pb = 0, acc = 0, pacc = 0;
@@ -569,7 +583,53 @@ __global__ void __launch_bounds__(FUSE ? NTHREADS_FUSED : 64 + 32 * EPW, 1) conv
             }
             TRACE(1, 2, t);
             tc_fence_after();
-            const int ntap_kb = is_res ? 1 : ntaps;
+            int ntap_kb = is_res ? 1 : ntaps;
+            if constexpr (PK) {
+              if (!is_res) {
+                // K-packed 24-channel convolution: the (tap, chunk) items back to back, two per K-step.  Per pair of taps
+                // (t, t+1) three K-steps:  (t: chunks 0,1)  ((t+1: chunk 0), (t: chunk 2))  (t+1: chunks 1,2)  -- the middle
+                // one straddles the taps, stored in that order so its K-chunk stride 2*astride - d stays positive; an odd
+                // last tap adds (chunks 0,1) and (chunk 2, zero chunk).  Start address and stride are uniform arithmetic
+                // on (tap, dilation): no table, everything stays in uniform registers.  The weights are resident.
+                if (first) {
+                  int s2 = sb, p2 = pb;
+                  for (int i = 0; i < ka.nstg; ++i) { mbar_wait(B_FULL(s2), p2); if (++s2 == NB) { s2 = 0; p2 ^= 1; } }
+                  tc_fence_after();
+                }
+                const uint32_t ast = (uint32_t)ka.astride;
+                const uint32_t dil = (uint32_t)(a.tap_off[1] - a.tap_off[0]);
+                const uint32_t L1 = ast << 16, L2 = (2u * ast - dil) << 16;
+                uint32_t base = a_lo_stage - a_lbo_word;   // start field (stage base + tap shift), stride field empty
+                uint32_t blo = b_lo, af = accum;
+                auto ks = [&](uint32_t alo) {
+                  const uint64_t bd = ((uint64_t)b_hi << 32) | blo;
+                  umma_bf16(d0, ((uint64_t)a_hi << 32) | alo, bd, idesc, af);
+                  if (MS >= 2) umma_bf16(d0 + bnc, ((uint64_t)a_hi << 32) | (alo + 128u), bd, idesc, af);
+                  if (MS == 4) {
+                    umma_bf16(d0 + 2 * bnc, ((uint64_t)a_hi << 32) | (alo + 256u), bd, idesc, af);
+                    umma_bf16(d0 + 3 * bnc, ((uint64_t)a_hi << 32) | (alo + 384u), bd, idesc, af);
+                  }
+                  blo += b_kstep;
+                  af = 1;
+                };
+                int tp = 0;
+                for (; tp + 1 < a.ntaps; tp += 2) {
+                  ks(base + L1);
+                  ks(base + dil + L2);
+                  ks(base + ast + dil + L1);
+                  base += 2u * dil;
+                }
+                if (tp < a.ntaps) {
+                  ks(base + L1);
+                  ks(base + 2u * ast + L1);
+                }
+                accum = 1;
+                sb += ka.nstg;                                   // resident: NB == stages per tile (wraps here when no identity stage follows)
+                b_lo += (uint32_t)ka.nstg * b_stage_lo;
+                if (sb >= NB) { sb -= NB; pb ^= 1; b_lo = b_lo0 + (uint32_t)sb * b_stage_lo; }
+                ntap_kb = 0;
+              }
+            }
             for (int tap = 0; tap < ntap_kb; ++tap) {
               const uint32_t sh_next = tapshift[tap + 1];   // one tap ahead: off the critical path
               if (!resident || first) {
@@ -615,14 +675,20 @@ __global__ void __launch_bounds__(FUSE ? NTHREADS_FUSED : 64 + 32 * EPW, 1) conv
       // specialised (MSUB, K-steps) pairs = the narrow AMP-block layers, where the issue loop is the limit
       using std::integral_constant;
       const int nk = (ka.debug & 2) ? -1 : ka.KC / 2;
-      if (ka.MSUB == 4 && nk == 2) run(integral_constant<int, 4>{}, integral_constant<int, 2>{});        // C = 24
-      else if (ka.MSUB == 4 && nk == 3) run(integral_constant<int, 4>{}, integral_constant<int, 3>{});   // C = 48
-      else if (ka.MSUB == 2 && nk == 6) run(integral_constant<int, 2>{}, integral_constant<int, 6>{});   // C = 96
-      else if (ka.MSUB == 1 && nk == 4) run(integral_constant<int, 1>{}, integral_constant<int, 4>{});   // C >= 192 (KC = 8)
-      else if (ka.MSUB == 2 && nk == 4) run(integral_constant<int, 2>{}, integral_constant<int, 4>{});
-      else if (ka.MSUB == 4) run(integral_constant<int, 4>{}, integral_constant<int, 0>{});
-      else if (ka.MSUB == 2) run(integral_constant<int, 2>{}, integral_constant<int, 0>{});
-      else run(integral_constant<int, 1>{}, integral_constant<int, 0>{});
+      using no_pk = std::false_type;
+      if (ka.packed && !FUSE) {   // K-packed 24-channel layer (nk == 2)
+        if (ka.MSUB == 4) run(integral_constant<int, 4>{}, integral_constant<int, 2>{}, std::true_type{});
+        else if (ka.MSUB == 2) run(integral_constant<int, 2>{}, integral_constant<int, 2>{}, std::true_type{});
+        else run(integral_constant<int, 1>{}, integral_constant<int, 2>{}, std::true_type{});
+      }
+      else if (ka.MSUB == 4 && nk == 2) run(integral_constant<int, 4>{}, integral_constant<int, 2>{}, no_pk{});        // C = 24
+      else if (ka.MSUB == 4 && nk == 3) run(integral_constant<int, 4>{}, integral_constant<int, 3>{}, no_pk{});   // C = 48
+      else if (ka.MSUB == 2 && nk == 6) run(integral_constant<int, 2>{}, integral_constant<int, 6>{}, no_pk{});   // C = 96
+      else if (ka.MSUB == 1 && nk == 4) run(integral_constant<int, 1>{}, integral_constant<int, 4>{}, no_pk{});   // C >= 192 (KC = 8)
+      else if (ka.MSUB == 2 && nk == 4) run(integral_constant<int, 2>{}, integral_constant<int, 4>{}, no_pk{});
+      else if (ka.MSUB == 4) run(integral_constant<int, 4>{}, integral_constant<int, 0>{}, no_pk{});
+      else if (ka.MSUB == 2) run(integral_constant<int, 2>{}, integral_constant<int, 0>{}, no_pk{});
+      else run(integral_constant<int, 1>{}, integral_constant<int, 0>{}, no_pk{});
     }
     __syncwarp();
   } else if (warp < 2 + epiw) {
@@ -967,6 +1033,32 @@ __global__ void repack_umma_kernel(const float* __restrict__ wt, T* __restrict__
 }
 
 // identity images [kb][chunk KC][n BN][8] appended after the conv images of a square (Cin == N), single-n-tile layer
+// K-packed image of a 24-channel layer: [stage][slot 0..3][n BN][8]; slot = (K-step within the stage, half); K-step s holds
+// the items 2s and 2s+1 of the (tap, chunk) sequence, a pair that straddles two taps in swapped order (see the issuer's table)
+template <typename T>
+__global__ void repack_umma_packed_kernel(const float* __restrict__ wt, T* __restrict__ img, int ntaps, int Cin, int N,
+                                          int BN, int nstg, const float* __restrict__ out_scale, const float* __restrict__ in_scale) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t total = (size_t)nstg * 4 * BN * 8;
+  if (idx >= total) return;
+  const int e = idx & 7;
+  size_t r = idx >> 3;
+  const int nn = r % BN; r /= BN;
+  const int slot = r % 4;
+  const int stage = r / 4;
+  const int sidx = 2 * stage + (slot >> 1), half = slot & 1, nitems = 3 * ntaps;
+  const int i0 = 2 * sidx, i1 = 2 * sidx + 1;
+  const bool swapped = i1 < nitems && (i0 / 3) != (i1 / 3);
+  const int item = half == 0 ? (swapped ? i1 : i0) : (swapped ? i0 : i1);
+  float v = 0.f;
+  if (item < nitems && nn < N) {
+    const int tap = item / 3, ci = (item - 3 * tap) * 8 + e;
+    v = wt[((size_t)tap * Cin + ci) * N + nn];
+    if (out_scale) v *= out_scale[nn];
+    if (in_scale) v *= in_scale[ci];
+  }
+  img[idx] = from_f32<T>(v);
+}
 template <typename T>
 __global__ void identity_umma_kernel(T* __restrict__ img, int N, int KC, int NKB, int BN, float value,
                                      const float* __restrict__ diag /* optional per-channel factor */) {
@@ -1003,13 +1095,14 @@ void tap_range(const ConvArgs& a, int& mn, int& mx) {
 // Launch-time configuration for a given number of 128-row sub-tiles per tile.
 bool configure(const ConvArgs& a, int msub, UmmaKernelArgs& ka, size_t& smem_bytes) {
   const int N = a.u * a.Cout;
-  const UmmaTiling t = make_tiling(a.ntaps, a.Cin, N, a.bn_small != 0);
+  const UmmaTiling t = make_tiling(a.ntaps, a.Cin, N, a.bn_small != 0, a.k_packed != 0);
   if (!t.ok) return false;
   int mn, mx;
   tap_range(a, mn, mx);
   if (mx - mn > MAXSPAN || -mn > BVG_GUARD || mx > BVG_GUARD) return false;
   ka.c = a;
   ka.KC = t.KC; ka.NKB = t.NKB; ka.BN = t.BN; ka.BNC = t.BNC; ka.NT = t.NT;
+  ka.packed = t.packed; ka.nks = t.nks; ka.nstg = t.nstg;
   ka.minoff = mn; ka.span = mx - mn;
   ka.MSUB = msub;
   ka.ACC = 512 / (ka.MSUB * ka.BNC);
@@ -1028,7 +1121,7 @@ bool configure(const ConvArgs& a, int msub, UmmaKernelArgs& ka, size_t& smem_byt
   ka.acc_mma = use_acc_mma(a, t) ? 1 : 0;
   ka.n_extra = ka.res_mma + ka.acc_mma;
   // pipeline depths within the smem budget
-  const int total_b = t.NKB * (a.ntaps + ka.n_extra);
+  const int total_b = t.NKB * (t.nstg + ka.n_extra);
   ka.NA = t.NKB > 1 ? 2 : 3;
   ka.b_resident = 0;
   static const int allow_resident = env_int("BVG_CONV_RESIDENT", 1);
@@ -1047,8 +1140,9 @@ bool configure(const ConvArgs& a, int msub, UmmaKernelArgs& ka, size_t& smem_byt
     if (nb < 1) return false;
     ka.NB = nb;
   }
+  if (ka.packed && !ka.b_resident) return false;   // the K-packed issue path assumes resident weights
   smem_bytes = (size_t)ka.NA * ka.a_stage_bytes + (size_t)ka.NB * ka.b_stage_bytes +
-               8 * (size_t)(2 * ka.NA + 2 * ka.NB + 2 * ka.ACC) + 128 + 4 * SBIAS_MAX;
+               8 * (size_t)(2 * ka.NA + 2 * ka.NB + 2 * ka.ACC) + 192 + 4 * SBIAS_MAX;
   if (smem_bytes < 120 * 1024) smem_bytes = 120 * 1024;   // one persistent CTA per SM (it owns the TMEM)
   return smem_bytes <= (size_t)SMEM_MAX;
 }
@@ -1063,6 +1157,7 @@ bool configure_fused(const ConvArgs& a, int msub, UmmaKernelArgs& ka, size_t& sm
   if (mx - mn > MAXSPAN || -mn > BVG_GUARD || mx > BVG_GUARD) return false;
   ka.c = a;
   ka.KC = t.KC; ka.NKB = t.NKB; ka.BN = t.BN; ka.BNC = t.BNC; ka.NT = t.NT;
+  ka.packed = 0; ka.nks = 0; ka.nstg = a.ntaps;
   ka.minoff = mn; ka.span = mx - mn;
   ka.MSUB = msub;
   ka.ACC = 512 / (ka.MSUB * ka.BNC);
@@ -1107,23 +1202,36 @@ bool configure_fused(const ConvArgs& a, int msub, UmmaKernelArgs& ka, size_t& sm
     if (nb < 2 && total_b >= 2) return false;
     ka.NB = nb;
   }
-  smem_bytes = fixed + (size_t)ka.NB * ka.b_stage_bytes + 8 * (size_t)(3 * ka.NA + 2 * ka.NB + 2 * ka.ACC + 2 * ka.NR) + 128 + 4 * SBIAS_MAX;
+  smem_bytes = fixed + (size_t)ka.NB * ka.b_stage_bytes + 8 * (size_t)(3 * ka.NA + 2 * ka.NB + 2 * ka.ACC + 2 * ka.NR) + 192 + 4 * SBIAS_MAX;
   if (smem_bytes < 120 * 1024) smem_bytes = 120 * 1024;
   return smem_bytes <= (size_t)SMEM_MAX;
 }
 
 }  // namespace
 
-size_t umma_weight_image_bytes(int ntaps, int Cin, int N, bool small) {
-  UmmaTiling t = make_tiling(ntaps, Cin, N, small);
+bool umma_k_packed_default(int Cin, int N) {
+  static const int on = [] {
+    const char* f = getenv("BVG_FUSE_ACT");   // the experimental fused kernel reads the unpacked image
+    if (f && atoi(f)) return 0;
+    return env_int("BVG_CONV_PACKK", 1);
+  }();
+  return on && Cin == 24 && N <= 256;
+}
+
+size_t umma_weight_image_bytes(int ntaps, int Cin, int N, bool small, bool packed) {
+  UmmaTiling t = make_tiling(ntaps, Cin, N, small, packed);
   if (!t.ok) return 0;
-  return (size_t)(t.NT * t.NKB * ntaps + (has_identity(t, Cin, N) ? 2 * t.NKB : 0)) * t.KC * t.BN * 16;
+  return (size_t)(t.NT * t.NKB * t.nstg + (has_identity(t, Cin, N) ? 2 * t.NKB : 0)) * t.KC * t.BN * 16;
 }
 
 template <typename T>
 static void repack_umma_t(const float* wp_tap_major, T* img, const UmmaTiling& t, int ntaps, int Cin, int N, float acc_img_scale,
                           const float* out_scale, const float* in_scale, const float* res_diag, cudaStream_t s) {
-  size_t total = (size_t)t.NT * t.NKB * ntaps * t.KC * t.BN * 8;
+  size_t total = (size_t)t.NT * t.NKB * t.nstg * t.KC * t.BN * 8;
+  if (t.packed)
+    repack_umma_packed_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(wp_tap_major, img, ntaps, Cin, N, t.BN, t.nstg, out_scale,
+                                                                                in_scale);
+  else
   repack_umma_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(wp_tap_major, img, ntaps, Cin, N, t.KC, t.NKB, t.BN, t.NT,
                                                                        out_scale, in_scale);
   if (has_identity(t, Cin, N)) {
@@ -1135,8 +1243,9 @@ static void repack_umma_t(const float* wp_tap_major, T* img, const UmmaTiling& t
 }
 
 cudaError_t launch_repack_umma(const float* wp_tap_major, void* img, int dtype, int ntaps, int Cin, int N, float acc_img_scale,
-                               bool small, cudaStream_t s, const float* out_scale, const float* in_scale, const float* res_diag) {
-  UmmaTiling t = make_tiling(ntaps, Cin, N, small);
+                               bool small, cudaStream_t s, const float* out_scale, const float* in_scale, const float* res_diag,
+                               bool packed) {
+  UmmaTiling t = make_tiling(ntaps, Cin, N, small, packed);
   if (!t.ok || (dtype != 1 && dtype != 2)) return cudaErrorInvalidValue;
   if (dtype == 1) repack_umma_t(wp_tap_major, (__nv_bfloat16*)img, t, ntaps, Cin, N, acc_img_scale, out_scale, in_scale, res_diag, s);
   else repack_umma_t(wp_tap_major, (__half*)img, t, ntaps, Cin, N, acc_img_scale, out_scale, in_scale, res_diag, s);
@@ -1167,7 +1276,7 @@ int conv_umma_fused_msub(const ConvArgs& a, bool force) {
   // activation is FP32-pipe bound and 10 activation warps per SM cannot outrun the stand-alone kernel.
   static const int enabled = env_int("BVG_FUSE_ACT", 0);
   static const int forced = env_int("BVG_CONV_MSUB", 0);
-  if (!(enabled || force) || !a.act_alpha || a.dtype == 2 || a.bn_small) return 0;   // the fused activation warps are bf16 only
+  if (!(enabled || force) || !a.act_alpha || a.dtype == 2 || a.bn_small || a.k_packed) return 0;   // the fused activation warps are bf16 only
   const UmmaTiling t = make_tiling(a.ntaps, a.Cin, a.Cout);
   if (!t.ok || t.NT != 1 || a.u != 1) return 0;
   for (int msub = 4; msub >= 1; msub >>= 1) {

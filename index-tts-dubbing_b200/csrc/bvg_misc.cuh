@@ -18,12 +18,13 @@ cudaError_t launch_snake_params(const float* la, const float* lb, float* alpha, 
                                 cudaStream_t s);
 // 16-bit UMMA weight images (bvg_conv_umma.cu); dtype 1 = bf16, 2 = fp16
 // small: the 64-column n-tile images of the small-batch variant (wide layers only)
-size_t umma_weight_image_bytes(int ntaps, int Cin, int N, bool small = false);
+size_t umma_weight_image_bytes(int ntaps, int Cin, int N, bool small = false, bool packed = false);
+bool umma_k_packed_default(int Cin, int N);   // whether bvg_forward's image of such a layer is K-packed (BVG_CONV_PACKK, default 1)
 // out_scale [N] / in_scale [Cin]: optional per-channel factors folded into the image (fp32, before rounding);
 // res_diag [N]: optional diagonal of the residual identity image (layers whose residual goes through the tensor core)
 cudaError_t launch_repack_umma(const float* wp_tap_major, void* img, int dtype, int ntaps, int Cin, int N, float acc_img_scale,
                                bool small, cudaStream_t s, const float* out_scale = nullptr, const float* in_scale = nullptr,
-                               const float* res_diag = nullptr);
+                               const float* res_diag = nullptr, bool packed = false);
 cudaError_t launch_scale_vec(const float* x, const float* scale, float* y, int n, cudaStream_t s);   // y = x * scale
 cudaError_t launch_zero_guards(void* buf, int esize, const SegDesc* seg, int B, int C, int R, cudaStream_t s);
 // every packed buffer of a plan in one launch
