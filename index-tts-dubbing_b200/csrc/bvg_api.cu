@@ -531,7 +531,8 @@ static int finalize_act(bvg_handle* h, ActLayer& A, cudaStream_t s) {
 //     s_m x_m (s_m = 2 alpha of act1_m): s_m into c2_{m-1}'s output channels and bias, 1 / s_m into c1_m's input channels,
 //     and a per-channel factor on each c2's residual input (s_{m+1} / s_m, with s = 1 where nothing is folded: x_0 is the
 //     stage input shared by the nk resblocks, and the last c2 accumulates into the unscaled stage output) -- the diagonal of
-//     the residual identity image for the narrow layers, a multiply in the epilogue for the wide ones.
+//     the residual identity image.  Done for the narrow layers (C <= 96) only: in the wide ones the residual is added in the
+//     epilogue and the extra per-channel multiply there costs more than the activation saves.
 // A layer whose alpha leaves [1/64, 64] keeps the plain kernel (fp16 range).  The fp32 parity mode, the per-op entry points
 // and the experimental fused kernel use the unfolded parameters.
 static int fold_activation_scales(bvg_handle* h, cudaStream_t s) {
@@ -572,7 +573,10 @@ static int fold_activation_scales(bvg_handle* h, cudaStream_t s) {
       ActLayer& A = h->acts[rb * 2 * nd + a];
       A.prescaled = false;
       const bool is_act2 = a & 1;
-      const bool want = enabled >= 1 && (is_act2 || (enabled >= 2 && a >= 2));   // act1 of m = 0 reads the shared stage input
+      // act1 of m = 0 reads the shared stage input.  act1 of m >= 1: only where the residual goes through the identity MMA
+      // (C <= 96): in the wide layers the per-channel residual factor is an epilogue multiply that costs more than the
+      // activation saves (measured: +15 us per c2 launch at C = 192); BVG_ACT_FOLD=3 folds them anyway.
+      const bool want = enabled >= 1 && (is_act2 || (a >= 2 && (enabled >= 3 || (enabled >= 2 && C <= 96))));
       if (!want) continue;
       std::vector<float> al;
       if (alpha_host(A, al)) return 1;

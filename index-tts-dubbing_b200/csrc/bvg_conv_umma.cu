@@ -537,9 +537,10 @@ __global__ void __launch_bounds__(FUSE ? NTHREADS_FUSED : 64 + 32 * EPW, 1) conv
     // loop is kept to a handful of instructions -- 32-bit descriptor words advanced incrementally, the
     // per-tap row shifts read from a small shared-memory table one tap ahead, MSUB a compile-time constant.
     if (elect_one()) {
-      uint32_t* tapshift = reinterpret_cast<uint32_t*>(tmem_slot + 2);   // [ntaps + 1] row shifts (16-byte units)
-      for (int tp = 0; tp < a.ntaps; ++tp) tapshift[tp] = (uint32_t)(a.tap_off[tp] - ka.minoff);
-      tapshift[a.ntaps] = 0;
+      // tap offsets are an arithmetic progression (dilated conv: step d; transposed conv: step -1; checked in configure):
+      // the per-tap row shift advances by a uniform add -- no table, no vector-to-uniform register moves in the issue loop
+      const uint32_t sh0 = (uint32_t)(a.tap_off[0] - ka.minoff);
+      const uint32_t sh_step = a.ntaps > 1 ? (uint32_t)(a.tap_off[1] - a.tap_off[0]) : 0u;
       auto run = [&](auto ms_tag, auto nk_tag, auto pk_tag) {
         constexpr int MS = decltype(ms_tag)::value;
         constexpr int NK = decltype(nk_tag)::value;   // K-steps per tap known at compile time (0 = runtime loop)
@@ -574,7 +575,7 @@ __global__ void __launch_bounds__(FUSE ? NTHREADS_FUSED : 64 + 32 * EPW, 1) conv
           uint32_t accum = 0;
           for (int kb = 0; kb < nkbt; ++kb) {
             const bool is_res = kb >= NKB;   // residual tile x identity weights
-            uint32_t sh = is_res ? res_shift : tapshift[0];
+            uint32_t sh = is_res ? res_shift : sh0;
             if constexpr (FUSE) {
               if (is_res) { mbar_wait(AR_FULL(sa), (ph_res >> sa) & 1u); ph_res ^= 1u << sa; }
               else { mbar_wait(A_FULL(sa), (ph_act >> sa) & 1u); ph_act ^= 1u << sa; }
@@ -631,7 +632,6 @@ __global__ void __launch_bounds__(FUSE ? NTHREADS_FUSED : 64 + 32 * EPW, 1) conv
               }
             }
             for (int tap = 0; tap < ntap_kb; ++tap) {
-              const uint32_t sh_next = tapshift[tap + 1];   // one tap ahead: off the critical path
               if (!resident || first) {
                 mbar_wait(B_FULL(sb), pb);
                 tc_fence_after();
@@ -660,7 +660,7 @@ __global__ void __launch_bounds__(FUSE ? NTHREADS_FUSED : 64 + 32 * EPW, 1) conv
               if (!resident) umma_commit(B_EMPTY(sb));
               b_lo += b_stage_lo;
               if (++sb == NB) { sb = 0; pb ^= 1; b_lo = b_lo0; }
-              sh = sh_next;
+              sh += sh_step;
             }
             umma_commit(A_EMPTY(sa));
             a_lo_stage += a_stage_lo;
@@ -790,13 +790,11 @@ __global__ void __launch_bounds__(FUSE ? NTHREADS_FUSED : 64 + 32 * EPW, 1) conv
 #pragma unroll
             for (int j = 0; j < 8; ++j) bv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
           }
-          float4 rsc[8];   // per-channel residual factors (pre-scaled residual stream, see fold_activation_scales)
+          // per-channel residual factors (pre-scaled residual stream, see fold_activation_scales): read per 8-channel unit
+          // where they are used (the same addresses for the whole warp, L1 hits) -- holding all 32 in registers made the
+          // kernel spill
           const bool rscaled = rg != nullptr && a.res_scale != nullptr;
-          if (rscaled) {
-            const float4* g4 = reinterpret_cast<const float4*>(a.res_scale + nbase);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) rsc[j] = nbase + 4 * j < N ? __ldg(g4 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
+          const float4* rs4 = reinterpret_cast<const float4*>(a.res_scale + nbase);
           uint4 resv[4], oldv[4];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
@@ -812,7 +810,7 @@ __global__ void __launch_bounds__(FUSE ? NTHREADS_FUSED : 64 + 32 * EPW, 1) conv
             v[4] = __uint_as_float(r[8 * u + 4]) + bv[2 * u + 1].x; v[5] = __uint_as_float(r[8 * u + 5]) + bv[2 * u + 1].y;
             v[6] = __uint_as_float(r[8 * u + 6]) + bv[2 * u + 1].z; v[7] = __uint_as_float(r[8 * u + 7]) + bv[2 * u + 1].w;
             if (rg && ok[u]) {
-              if (rscaled) unpack_fma<F16>(resv[u], v, rsc[2 * u], rsc[2 * u + 1]);
+              if (rscaled) unpack_fma<F16>(resv[u], v, __ldg(rs4 + 2 * u), __ldg(rs4 + 2 * u + 1));
               else unpack_add<F16>(resv[u], v);
             }
 #pragma unroll
@@ -1100,6 +1098,8 @@ bool configure(const ConvArgs& a, int msub, UmmaKernelArgs& ka, size_t& smem_byt
   int mn, mx;
   tap_range(a, mn, mx);
   if (mx - mn > MAXSPAN || -mn > BVG_GUARD || mx > BVG_GUARD) return false;
+  for (int j = 2; j < a.ntaps; ++j)   // the issue loop advances the tap shift by a constant step
+    if (a.tap_off[j] - a.tap_off[j - 1] != a.tap_off[1] - a.tap_off[0]) return false;
   ka.c = a;
   ka.KC = t.KC; ka.NKB = t.NKB; ka.BN = t.BN; ka.BNC = t.BNC; ka.NT = t.NT;
   ka.packed = t.packed; ka.nks = t.nks; ka.nstg = t.nstg;
