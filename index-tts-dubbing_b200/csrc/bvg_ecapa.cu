@@ -123,6 +123,62 @@ __global__ void __launch_bounds__(128) econv_kernel(const EConv a) {
   }
 }
 
+// The same convolution for a SHORT reduction (R = Cin * K <= 192: the 21 sequential 64 -> 64, k = 3 Res2Net convolutions of a
+// prompt).  The pipelined kernel above pays one exposed global-load latency per 16-step stage (12 stages, 17 us per launch);
+// here a block loads its whole weight slab [R][32] and input slab [R][16] once -- one latency -- and then only computes.
+// 128 threads, 32 x 16 output tile, 2 x 2 outputs per thread.
+constexpr int SR = 192, SBM = 32, SBN = 16;
+__global__ void __launch_bounds__(128) econv_small_kernel(const EConv a) {
+  __shared__ float Ws[SR][SBM + 1];
+  __shared__ float Xs[SR][SBN + 1];
+  const int t0 = blockIdx.x * SBN, co0 = blockIdx.y * SBM, b = blockIdx.z;
+  const int tid = threadIdx.x, tx = tid & 7, ty = tid >> 3;
+  const int K = a.K, R = a.Cin * K, pad = a.dil * (K - 1) / 2;
+  const float* xb = a.x + (size_t)b * a.xb;
+  const float* x2b = a.x2 ? a.x2 + (size_t)b * a.x2b : nullptr;
+#pragma unroll 8
+  for (int idx = tid; idx < R * SBM; idx += 128) {          // consecutive threads read consecutive r of one weight row
+    const int row = idx / R, r = idx - row * R;
+    Ws[r][row] = co0 + row < a.Cout ? __ldg(a.w + (size_t)(co0 + row) * a.wrs + a.wco + r) : 0.f;
+  }
+#pragma unroll 8
+  for (int idx = tid; idx < R * SBN; idx += 128) {
+    const int r = idx / SBN, j = idx - r * SBN;
+    const int ci = r / K, kk = r - ci * K;
+    const int t = reflect(t0 + j + kk * a.dil - pad, a.T);
+    float v = xb[(size_t)ci * a.T + t];
+    if (x2b) v += x2b[(size_t)ci * a.T + t];
+    Xs[r][j] = v;
+  }
+  __syncthreads();
+  float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+#pragma unroll 8
+  for (int r = 0; r < R; ++r) {
+    const float w0 = Ws[r][ty * 2], w1 = Ws[r][ty * 2 + 1], x0 = Xs[r][tx * 2], x1 = Xs[r][tx * 2 + 1];
+    acc[0][0] = fmaf(w0, x0, acc[0][0]); acc[0][1] = fmaf(w0, x1, acc[0][1]);
+    acc[1][0] = fmaf(w1, x0, acc[1][0]); acc[1][1] = fmaf(w1, x1, acc[1][1]);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int co = co0 + ty * 2 + i;
+    if (co >= a.Cout) continue;
+    float bv = a.bias ? a.bias[co] : 0.f;
+    if (a.bias_b) bv += a.bias_b[(size_t)b * a.Cout + co];
+    const float sc = a.scale ? a.scale[co] : 1.f, sh = a.scale ? a.shift[co] : 0.f;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int t = t0 + tx * 2 + j;
+      if (t >= a.T) continue;
+      float v = acc[i][j] + bv;
+      if (a.relu) v = fmaxf(v, 0.f);
+      v = v * sc + sh;
+      if (a.post == 1) v = tanhf(v);
+      else if (a.post == 2) v = 1.f / (1.f + expf(-v));
+      a.y[(size_t)b * a.yb + (size_t)co * a.T + t] = v;
+    }
+  }
+}
+
 // Length-1 "convolutions" (SE block, final fc) and time-constant input channels folded into a bias: one warp per output,
 // y[b, co] = post(relu?(sum_ci w[co*wrs + wco + ci] * x[b*xb + ci] + bias[co]))
 __global__ void __launch_bounds__(256) egemv_kernel(const float* __restrict__ x, long long xb, const float* __restrict__ w, long long wrs,
@@ -291,8 +347,13 @@ struct Runner {
             int dil, int relu, int post) {
     if (K > 5 || dil * (K - 1) / 2 > MAXPAD) { err = cudaErrorInvalidValue; return; }
     EConv a{x, xb, x2, x2b, w, wrs, wco, bias, bias_b, scale, shift, y, yb, Cin, Cout, T_, K, dil, relu, post};
-    dim3 grid((T_ + BN - 1) / BN, (Cout + BM - 1) / BM, B);
-    econv_kernel<<<grid, 128, 0, s>>>(a);
+    if (Cin * K <= SR && T_ > 1) {   // short reduction: everything preloaded (Res2Net convolutions)
+      dim3 grid((T_ + SBN - 1) / SBN, (Cout + SBM - 1) / SBM, B);
+      econv_small_kernel<<<grid, 128, 0, s>>>(a);
+    } else {
+      dim3 grid((T_ + BN - 1) / BN, (Cout + BM - 1) / BM, B);
+      econv_kernel<<<grid, 128, 0, s>>>(a);
+    }
     check();
   }
   // length-1 sequence: y[b, :] = post(relu?(W[:, wco : wco + Cin] x[b, :] + bias))
