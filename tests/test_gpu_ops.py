@@ -125,6 +125,8 @@ UMMA_CONV_CASES = [  # (B, Cin, Cout, T, k, d)
     (1, 64, 64, 128, 3, 1), (1, 64, 64, 300, 3, 1), (2, 192, 192, 260, 7, 3), (1, 96, 96, 515, 11, 5),
     (1, 48, 48, 700, 7, 5), (1, 24, 24, 1000, 11, 1), (1, 128, 128, 130, 3, 3), (1, 256, 768, 300, 3, 5),
     (2, 384, 384, 200, 11, 5), (1, 1024, 1536, 100, 7, 1), (3, 768, 768, 77, 7, 1),
+    # more 512-row tiles than SMs: persistent CTAs walk several tiles (stage rings wrap); K-packed 24-channel layers, odd / even taps
+    (1, 24, 24, 100000, 11, 5), (1, 24, 24, 90000, 7, 3), (2, 24, 24, 45000, 3, 1), (1, 48, 48, 90000, 3, 1),
 ]
 
 
@@ -186,6 +188,7 @@ def test_conv_transpose1d_tcgen05_bf16(case):
 ACT_CONV_CASES = [  # (B, C, T, k, d): AMPBlock1 half-steps (Activation1d -> Conv1d [+ residual])
     (1, 24, 700, 3, 1), (1, 24, 100, 11, 5), (2, 48, 333, 7, 3), (2, 96, 300, 11, 5), (1, 192, 400, 3, 1),
     (3, 24, 7, 3, 1), (1, 384, 90, 7, 1),
+    (1, 24, 80000, 11, 1),   # several tiles per persistent CTA, with and without the residual identity stages
 ]
 
 
