@@ -43,8 +43,11 @@ enum { BVG_F32 = 0, BVG_BF16 = 1, BVG_F16 = 2 };
 enum {
   BVG_MODE_FP32 = 0, /* parity mode: fp32 storage, fp32 FFMA convolutions (CUDA cores)          */
   BVG_MODE_BF16 = 1, /* performance mode: bf16 storage, tcgen05 bf16 MMA with fp32 accumulation  */
-  BVG_MODE_F16 = 2   /* performance mode: fp16 storage (3 more mantissa bits, saturating stores), tcgen05 f16 MMA with
+  BVG_MODE_F16 = 2,  /* performance mode: fp16 storage (3 more mantissa bits, saturating stores), tcgen05 f16 MMA with
                         fp32 accumulation -- what the reference runs under torch.amp.autocast(float16), infer.py:456,613 */
+  BVG_MODE_FP32_TC = 3 /* parity mode on the tensor cores: fp32 storage and activations; every convolution as three bf16
+                        tcgen05 products x_hi w_hi + x_lo w_hi + x_hi w_lo (x = hi + lo, w = hi + lo to 16 bits each) with
+                        fp32 accumulation -- meets the 1e-3 gate of the fp32 mode without the FFMA convolutions */
 };
 
 /* memory layout of the per-op test entry points */

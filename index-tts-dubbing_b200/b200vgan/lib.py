@@ -10,7 +10,7 @@ from typing import Optional
 
 from . import build as _build
 
-MODE_FP32, MODE_BF16, MODE_F16 = 0, 1, 2
+MODE_FP32, MODE_BF16, MODE_F16, MODE_FP32_TC = 0, 1, 2, 3
 F32, BF16, F16 = 0, 1, 2
 MAX_UPS, MAX_KERNELS, MAX_DILATIONS = 8, 4, 4
 

@@ -973,8 +973,10 @@ int conv_op(bool transposed, const float* x, const float* w, const float* bias, 
   ConvLayer L;
   L.transposed = transposed; L.Cin = Cin; L.Cout = Cout; L.k = k; L.d = d; L.u = u; L.setup();
   if (!transposed && (k - 1) / 2 * d > BVG_GUARD - 6) return fail("conv op: halo exceeds guard rows");
-  if (mode != BVG_MODE_FP32 && mode != BVG_MODE_BF16 && mode != BVG_MODE_F16) return fail("conv op: unknown mode %d", mode);
-  const int dt = mode == BVG_MODE_FP32 ? 0 : (mode == BVG_MODE_BF16 ? 1 : 2);
+  if (mode != BVG_MODE_FP32 && mode != BVG_MODE_BF16 && mode != BVG_MODE_F16 && mode != BVG_MODE_FP32_TC)
+    return fail("conv op: unknown mode %d", mode);
+  const bool tc32 = mode == BVG_MODE_FP32_TC;   // fp32 storage, split-bf16 operands on the tensor cores
+  const int dt = (mode == BVG_MODE_FP32 || tc32) ? 0 : (mode == BVG_MODE_BF16 ? 1 : 2);
   const size_t es = dt == 0 ? 4 : 2;
   const int Tout = T * u;
   OpTemps tmp;
@@ -1014,7 +1016,7 @@ int conv_op(bool transposed, const float* x, const float* w, const float* bias, 
     if (tmp.alloc((void**)&prm, 2 * (size_t)Cin * sizeof(float))) return 1;
     CK(launch_snake_params(log_alpha, log_beta, prm, prm + Cin, Cin, s));
     a.act_alpha = prm; a.act_inv_beta = prm + Cin;
-    const int fm = mode == BVG_MODE_BF16 ? conv_umma_fused_msub(a, fused_out && *fused_out) : 0;
+    const int fm = mode == BVG_MODE_BF16 ? conv_umma_fused_msub(a, fused_out && *fused_out) : 0;   // (never in the fp32 modes)
     if (fused_out) *fused_out = fm ? 1 : 0;
     if (fm) {
       a.msub = fm;
@@ -1023,11 +1025,33 @@ int conv_op(bool transposed, const float* x, const float* w, const float* bias, 
       if (tmp.alloc(&ac, (size_t)Cin * Rin * es)) return 1;
       CK(cudaMemsetAsync(ac, 0, (size_t)Cin * Rin * es, s));
       ActArgs aa{xc, ac, prm, prm + Cin, seg_dev, Rin, Cin, B, T};
-      CK(launch_act_c8(aa, dt, mode == BVG_MODE_FP32, s));
+      CK(launch_act_c8(aa, dt, mode == BVG_MODE_FP32 || tc32, s));
       a.x = ac; a.act_alpha = nullptr; a.act_inv_beta = nullptr;
     }
   }
-  if (mode != BVG_MODE_FP32) {
+  if (tc32) {
+    // [hi | lo] split of the fp32 input, [W_hi; W_hi; W_lo] weight image, fp32 epilogue
+    void* xs; float* w3;
+    if (tmp.alloc(&xs, (size_t)Cin * Rin * 4) || tmp.alloc((void**)&w3, 3 * (size_t)Cin * Cout * k * sizeof(float))) return 1;
+    CK(cudaMemsetAsync(xs, 0, (size_t)Cin * Rin * 4, s));
+    CK(launch_split_c8((const float*)a.x, xs, seg_dev, B, Cin, Rin, T, s));
+    CK(launch_split3_weights(wt, w3, L.ntaps, Cin, L.N, s));
+    a.x = xs; a.dtype = 1; a.f32io = 1; a.split3_chunks = Cin / 8; a.Cin = 3 * Cin;
+    a.msub = conv_umma_default_msub(a);
+    std::vector<int> pf(B + 1, 0);
+    for (int b = 0; b < B; ++b) pf[b + 1] = pf[b] + (T + L.q_extra + 128 * a.msub - 1) / (128 * a.msub);
+    int* pf_dev;
+    if (tmp.alloc((void**)&pf_dev, pf.size() * sizeof(int))) return 1;
+    CK(cudaMemcpyAsync(pf_dev, pf.data(), pf.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+    CK(cudaStreamSynchronize(s));
+    a.tile_prefix = pf_dev; a.total_mt = pf[B];
+    size_t bytes = umma_weight_image_bytes(L.ntaps, 3 * Cin, L.N);
+    if (!bytes || !conv_umma_supported(a)) return fail("conv op: shape not supported by the tcgen05 kernel (fp32 tensor-core mode)");
+    if (tmp.alloc(&wu, bytes)) return 1;
+    CK(launch_repack_umma(w3, wu, 1, L.ntaps, 3 * Cin, L.N, 1.f, false, s));
+    a.w = wu;
+    CK(launch_conv_umma(a, s));
+  } else if (mode != BVG_MODE_FP32) {
     if (!a.act_alpha && !transposed && umma_k_packed_default(Cin, L.N)) a.k_packed = 1;   // as bvg_forward does (not with the fused kernel)
     if (!a.act_alpha && L.N >= 256) {   // same rule as bvg_forward: the small-batch variant when few CTAs would run
       int dev = 0, sms = 148;

@@ -55,6 +55,11 @@ struct ConvArgs {
   int msub;                 // 1, 2 or 4
   int bn_small;             // 1: `w` is the 64-column n-tile image (small-batch variant of a wide layer), msub must be 1
   int k_packed;             // 1: `w` is the K-packed image of a 24-channel layer (taps share K-steps, see make_tiling)
+  // fp32 tensor-core mode (bvg_conv_umma.cu, F32IO): x is a SPLIT tensor -- split3_chunks 8-channel chunks of bf16 "hi"
+  // values followed by as many chunks of bf16 "lo" residuals (x ~ hi + lo to 16 bits) -- and Cin counts 3 x the real input
+  // channels: the GEMM multiplies [hi | lo | hi] with the weight image [W_hi; W_hi; W_lo]; y / res are fp32 packed tensors
+  int f32io;
+  int split3_chunks;
   // fused Activation1d (tcgen05 kernel, bf16): when set, x is the RAW input and the kernel applies the
   // activation with these per-input-channel parameters while staging its A operand
   const float* act_alpha;

@@ -97,7 +97,7 @@ inline UmmaTiling make_tiling(int ntaps, int Cin, int N, bool small = false, boo
   const int cin_pad = round_up_i(Cin, 16);
   if (cin_pad % 64 == 0) { t.KC = 8; t.NKB = cin_pad / 64; }
   else if (cin_pad <= 128) { t.KC = cin_pad / 8; t.NKB = 1; }
-  else return t;
+  else { t.KC = 8; t.NKB = round_up_i(cin_pad, 64) / 64; }   // last k-block partly padding (zero weight rows; 3 x C of the split mode)
   // N tile: 256 columns by default -- a 128 x 256 x 16 MMA is the only cta_group::1 shape that runs at
   // the tensor-pipe floor (tools/umma_bench.cu) and it halves the A-tile re-reads per output column.
   static const int bnmax_env = [] { int v = env_int("BVG_CONV_BNMAX", 256); return (v == 128 || v == 192) ? v : 256; }();
@@ -329,7 +329,8 @@ struct UmmaKernelArgs {
 
 struct TileRef { int nt, b, q0; };
 
-template <bool FUSE, int EPW = EPIW, bool F16 = false>
+// F32IO: the fp32 tensor-core mode -- split [hi | lo] bf16 input, fp32 output / residual / accumulate (see ConvArgs::f32io)
+template <bool FUSE, int EPW = EPIW, bool F16 = false, bool F32IO = false>
 __global__ void __launch_bounds__(FUSE ? NTHREADS_FUSED : 64 + 32 * EPW, 1) conv_umma_kernel(const UmmaKernelArgs ka) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const ConvArgs& a = ka.c;
@@ -483,7 +484,9 @@ __global__ void __launch_bounds__(FUSE ? NTHREADS_FUSED : 64 + 32 * EPW, 1) conv
             mbar_expect_tx(A_FULL(sa), (uint32_t)(kcl * arows * 16));
             const uint32_t adst = smem_u32(a_smem + (size_t)sa * ka.a_stage_bytes);
             for (int c = 0; c < kcl; ++c) {
-              const __nv_bfloat16* src = xg + ((size_t)(kb * ka.KC + c) * a.Rx + row0c) * 8;
+              int cc = kb * ka.KC + c;
+              if (F32IO && cc >= 2 * a.split3_chunks) cc -= 2 * a.split3_chunks;   // third block of the split GEMM = the hi chunks again
+              const __nv_bfloat16* src = xg + ((size_t)cc * a.Rx + row0c) * 8;
               bulk_g2s(adst + (uint32_t)(c * ka.astride) * 16, src, (uint32_t)(arows * 16), A_FULL(sa));
             }
           }
@@ -736,6 +739,38 @@ __global__ void __launch_bounds__(FUSE ? NTHREADS_FUSED : 64 + 32 * EPW, 1) conv
         __syncwarp();   // tcgen05.ld is .sync.aligned: reconverge after the predicated stores below
         tmem_ld32_nowait(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * acc_cols + sub * ka.BNC + grp * 32), r);
         const int nbase = n0 + grp * 32;     // first GEMM column of this group
+        if constexpr (F32IO) {
+          // fp32 tensor-core mode: fp32 bias / residual / old output / store, plain and transposed layers in one path
+          float* yf = reinterpret_cast<float*>(a.y);
+          const float* rf = reinterpret_cast<const float*>(a.res);
+          tmem_ld_wait();
+          int phase = plain ? 0 : nbase / a.Cout, co = plain ? nbase : nbase - phase * a.Cout;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int orow = plain ? q : q * a.u + phase - a.p;
+            const bool okk = qok && nbase + 8 * u < N && orow >= 0 && orow < soc.len;
+            if (okk) {
+              const size_t off = ((size_t)(co >> 3) * a.Ry + soc.off + orow) * 8;
+              float v[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[8 * u + j]) + (biasp ? __ldg(biasp + co + j) : 0.f);
+              if (rf) {
+                const float4 r0 = *reinterpret_cast<const float4*>(rf + off), r1 = *reinterpret_cast<const float4*>(rf + off + 4);
+                v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w; v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
+              }
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] *= a.out_scale;
+              if (a.accumulate) {
+                const float4 o0 = *reinterpret_cast<const float4*>(yf + off), o1 = *reinterpret_cast<const float4*>(yf + off + 4);
+                v[0] += o0.x; v[1] += o0.y; v[2] += o0.z; v[3] += o0.w; v[4] += o1.x; v[5] += o1.y; v[6] += o1.z; v[7] += o1.w;
+              }
+              *reinterpret_cast<float4*>(yf + off) = make_float4(v[0], v[1], v[2], v[3]);
+              *reinterpret_cast<float4*>(yf + off + 4) = make_float4(v[4], v[5], v[6], v[7]);
+            }
+            co += 8;
+            if (!plain && co >= a.Cout) { co -= a.Cout; ++phase; }
+          }
+        } else
         if (simple) {
           // fast path (no residual / accumulate reads, batch-independent bias in shared memory): the
           // common case of the AMP-block convolutions -- bias, scale, convert, four 16-byte stores
@@ -1209,6 +1244,29 @@ bool configure_fused(const ConvArgs& a, int msub, UmmaKernelArgs& ka, size_t& sm
 
 }  // namespace
 
+// fp32 tensor-core mode: W' [tap][3 Cin][N] = [W_hi; W_hi; W_lo] with W_hi = bf16(W), W_lo = bf16(W - W_hi) (both exactly
+// representable, so the bf16 repack that follows does not round again)
+__global__ void split3_weights_kernel(const float* __restrict__ w, float* __restrict__ w3, int ntaps, int Cin, int N) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t total = (size_t)ntaps * Cin * N;
+  if (idx >= total) return;
+  const int n = idx % N;
+  size_t r = idx / N;
+  const int ci = r % Cin, tap = r / Cin;
+  const float v = w[idx];
+  const float hi = __bfloat162float(__float2bfloat16_rn(v));
+  const float lo = __bfloat162float(__float2bfloat16_rn(v - hi));
+  float* base = w3 + (size_t)tap * 3 * Cin * N;
+  base[(size_t)ci * N + n] = hi;
+  base[(size_t)(Cin + ci) * N + n] = hi;
+  base[(size_t)(2 * Cin + ci) * N + n] = lo;
+}
+cudaError_t launch_split3_weights(const float* w_tap_major, float* w3, int ntaps, int Cin, int N, cudaStream_t s) {
+  size_t total = (size_t)ntaps * Cin * N;
+  split3_weights_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(w_tap_major, w3, ntaps, Cin, N);
+  return cudaGetLastError();
+}
+
 bool umma_k_packed_default(int Cin, int N) {
   static const int on = [] {
     const char* f = getenv("BVG_FUSE_ACT");   // the experimental fused kernel reads the unpacked image
@@ -1276,7 +1334,7 @@ int conv_umma_fused_msub(const ConvArgs& a, bool force) {
   // activation is FP32-pipe bound and 10 activation warps per SM cannot outrun the stand-alone kernel.
   static const int enabled = env_int("BVG_FUSE_ACT", 0);
   static const int forced = env_int("BVG_CONV_MSUB", 0);
-  if (!(enabled || force) || !a.act_alpha || a.dtype == 2 || a.bn_small || a.k_packed) return 0;   // the fused activation warps are bf16 only
+  if (!(enabled || force) || !a.act_alpha || a.dtype == 2 || a.bn_small || a.k_packed || a.f32io) return 0;   // the fused activation warps are bf16 only
   const UmmaTiling t = make_tiling(a.ntaps, a.Cin, a.Cout);
   if (!t.ok || t.NT != 1 || a.u != 1) return 0;
   for (int msub = 4; msub >= 1; msub >>= 1) {
@@ -1325,6 +1383,7 @@ cudaError_t launch_conv_umma(const ConvArgs& a, cudaStream_t s) {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_umma_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_umma_kernel<false, EPIW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_umma_kernel<false, EPIW, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX);
     if (e != cudaSuccess) return e;
     sms_of_dev[dev] = n;
   }
@@ -1347,7 +1406,11 @@ cudaError_t launch_conv_umma(const ConvArgs& a, cudaStream_t s) {
   static const int epiw4 = env_int("BVG_CONV_EPIW", 8) == 4;
   dim3 grid(total_tiles < num_sms ? total_tiles : num_sms), block(fuse ? NTHREADS_FUSED : (epiw4 ? 64 + 32 * 4 : NTHREADS));
   cudaError_t le;
-  if (a.dtype == 2 && !fuse) le = launch_pdl(conv_umma_kernel<false, EPIW, true>, grid, dim3(NTHREADS), smem, s, ka);
+  if (a.f32io) {
+    if (fuse || a.dtype != 1 || a.k_packed || a.bn_small || a.split3_chunks * 24 != a.Cin) return cudaErrorInvalidValue;
+    le = launch_pdl(conv_umma_kernel<false, EPIW, false, true>, grid, dim3(NTHREADS), smem, s, ka);
+  }
+  else if (a.dtype == 2 && !fuse) le = launch_pdl(conv_umma_kernel<false, EPIW, true>, grid, dim3(NTHREADS), smem, s, ka);
   else if (fuse) le = launch_pdl(conv_umma_kernel<true>, grid, block, smem, s, ka);
   else if (epiw4) le = launch_pdl(conv_umma_kernel<false, 4>, grid, block, smem, s, ka);
   else le = launch_pdl(conv_umma_kernel<false>, grid, block, smem, s, ka);

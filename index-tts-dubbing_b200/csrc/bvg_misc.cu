@@ -175,6 +175,26 @@ __global__ void zero_guards_all_kernel(const GuardJobs jobs, int B) {
   for (int i = threadIdx.x; i < n; i += blockDim.x) p[i] = z;
 }
 
+// packed fp32 [C/8][R][8] -> split bf16 [2 C/8][R][8]: hi = bf16(x) in chunk c, lo = bf16(x - hi) in chunk C/8 + c
+__global__ void split_c8_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, const SegDesc* __restrict__ seg,
+                                int nch, int R, int max_len) {
+  const int b = blockIdx.z, chunk = blockIdx.y;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const SegDesc sd = seg[b];
+  if (t >= sd.len || t >= max_len) return;
+  const size_t row = (size_t)chunk * R + sd.off + t;
+  Vec8<float> v;
+  v.load(x + row * 8);
+  Vec8<__nv_bfloat16> hi, lo;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    hi.v[c] = __bfloat162float(__float2bfloat16_rn(v.v[c]));
+    lo.v[c] = v.v[c] - hi.v[c];
+  }
+  hi.store(y + row * 8);
+  lo.store(y + ((size_t)(nch + chunk) * R + sd.off + t) * 8);
+}
+
 __global__ void scale_vec_kernel(const float* __restrict__ x, const float* __restrict__ sc, float* __restrict__ y, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) y[i] = x[i] * sc[i];
@@ -183,6 +203,13 @@ __global__ void scale_vec_kernel(const float* __restrict__ x, const float* __res
 inline int nblk(size_t n, int t) { return (int)((n + t - 1) / t); }
 
 }  // namespace
+
+cudaError_t launch_split_c8(const float* x, void* y_split, const SegDesc* seg, int B, int C, int R, int max_len, cudaStream_t s) {
+  if (B <= 0 || max_len <= 0) return cudaSuccess;
+  dim3 grid(nblk(max_len, 256), C >> 3, B);
+  split_c8_kernel<<<grid, 256, 0, s>>>(x, (__nv_bfloat16*)y_split, seg, C >> 3, R, max_len);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_scale_vec(const float* x, const float* scale, float* y, int n, cudaStream_t s) {
   scale_vec_kernel<<<nblk(n, 256), 256, 0, s>>>(x, scale, y, n);

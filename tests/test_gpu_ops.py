@@ -232,3 +232,60 @@ def test_act_conv1d_cuda_core_fp32():
     y, fused = G.act_conv1d(x, la, lb, w, b, None, k, d, 0, want_fused=True)
     assert not fused
     np.testing.assert_allclose(y, ref, atol=3e-5, rtol=1e-5)
+
+
+# ---- fp32 tensor-core mode (BVG_MODE_FP32_TC = 3): fp32 storage, three bf16 tcgen05 products per convolution ----
+TC32_CONV_CASES = [(1, 64, 64, 300, 3, 1), (2, 192, 192, 260, 7, 3), (1, 96, 96, 515, 11, 5), (1, 48, 48, 700, 7, 5),
+                   (1, 24, 24, 1000, 11, 1), (1, 256, 768, 300, 3, 5), (1, 1024, 1536, 100, 7, 1), (3, 768, 768, 77, 7, 1),
+                   (1, 24, 24, 90000, 7, 3)]
+
+
+@pytest.mark.parametrize("case", TC32_CONV_CASES)
+def test_conv1d_tcgen05_fp32_split(case):
+    """x_hi w_hi + x_lo w_hi + x_hi w_lo with fp32 accumulation against the fp64 oracle on the UNROUNDED fp32 inputs."""
+    from tests import gpu_util as G
+    B, Cin, Cout, T, k, d = case
+    x, w, b, r = _conv_inputs(B, Cin, Cout, T, k, 3)
+    ref = O.conv1d(x.astype(np.float64), w.astype(np.float64), b.astype(np.float64), dilation=d,
+                   padding=O.get_padding(k, d)) + r
+    y = G.conv1d(x, w, b, r, k, d, 3)
+    scale = np.abs(ref).max()
+    err = np.abs(y - ref).max()
+    print("fp32-tc conv", case, "max-abs", err, "scale", scale)
+    assert err <= 5e-5 * scale, (err, scale)
+
+
+@pytest.mark.parametrize("case", [(1, 64, 32, 100, 8, 4), (1, 48, 24, 300, 4, 2), (2, 64, 32, 127, 16, 4), (1, 1536, 768, 40, 8, 4)])
+def test_conv_transpose1d_tcgen05_fp32_split(case):
+    from tests import gpu_util as G
+    B, Cin, Cout, T, k, u = case
+    rng = np.random.default_rng(4)
+    x = rng.standard_normal((B, Cin, T)).astype(np.float32)
+    w = (rng.standard_normal((Cin, Cout, k)) / np.sqrt(Cin * k / u)).astype(np.float32)
+    b = (0.1 * rng.standard_normal(Cout)).astype(np.float32)
+    ref = O.conv_transpose1d(x.astype(np.float64), w.astype(np.float64), b.astype(np.float64), u, (k - u) // 2)
+    y = G.conv_transpose1d(x, w, b, k, u, 3)
+    scale = np.abs(ref).max()
+    err = np.abs(y - ref).max()
+    print("fp32-tc conv-transpose", case, "max-abs", err, "scale", scale)
+    assert err <= 5e-5 * scale, (err, scale)
+
+
+@pytest.mark.parametrize("case", [(1, 24, 700, 3, 1), (2, 96, 300, 11, 5), (1, 192, 400, 3, 1)])
+def test_act_conv1d_tcgen05_fp32_split(case):
+    from tests import gpu_util as G
+    B, C, T, k, d = case
+    rng = np.random.default_rng(11)
+    x = rng.standard_normal((B, C, T)).astype(np.float32)
+    la = (0.3 * rng.standard_normal(C)).astype(np.float32)
+    lb = (0.3 * rng.standard_normal(C)).astype(np.float32)
+    w = (rng.standard_normal((C, C, k)) / np.sqrt(C * k)).astype(np.float32)
+    b = (0.1 * rng.standard_normal(C)).astype(np.float32)
+    r = rng.standard_normal((B, C, T)).astype(np.float32)
+    ref = O.conv1d(O.activation1d(x.astype(np.float64), la.astype(np.float64), lb.astype(np.float64)),
+                   w.astype(np.float64), b.astype(np.float64), dilation=d, padding=O.get_padding(k, d)) + r
+    y, fused = G.act_conv1d(x, la, lb, w, b, r, k, d, 3)
+    assert not fused
+    err = np.abs(y - ref).max()
+    print("fp32-tc act+conv", case, "max-abs", err, "scale", np.abs(ref).max())
+    assert err <= 1e-4 * np.abs(ref).max()
