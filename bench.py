@@ -472,6 +472,7 @@ def run_ours(args):
         e2e_emb_value = world * audio_s_per_step * args.steps / (e2e_emb_ms / 1e3)
         conv = prof["conv_tcgen05"] if prof["conv_tcgen05"]["launches"] else prof["conv_cuda_core"]
         tc = args.precision != "fp32" and prof["conv_tcgen05"]["launches"] > 0
+        f32 = args.precision in ("fp32", "fp32tc")
         conv_tflops = conv["flops"] / (conv["ms"] * 1e-3) / 1e12 if conv["ms"] > 0 else 0.0
         peak_tf = pk["bf16_tflops_sustained"]
         act = prof["activation1d"]
@@ -497,9 +498,9 @@ def run_ours(args):
         # the tensor-core-FIR modes; the FP32 pipe (31 lane-operations per element, 128 lanes per SM per clock) in fp32 mode.
         sm_mhz = (clocks or {}).get("sm_mhz") or 0
         if act["ms"] > 0 and sm_mhz:
-            esize = 4 if args.precision == "fp32" else 2
+            esize = 4 if f32 else 2
             elems = act["bytes"] / (2.0 * esize)
-            ops_per_elem, lanes, pipe = (31.0, 128, "fp32") if args.precision == "fp32" else (2.0, 16, "mufu")
+            ops_per_elem, lanes, pipe = (31.0, 128, "fp32") if f32 else (2.0, 16, "mufu")
             ach = ops_per_elem * elems / (act["ms"] * 1e-3) / 1e12
             peak = 148 * lanes * sm_mhz * 1e6 / 1e12
             roofline_act["compute_pipe"] = {"pipe": pipe, "achieved_Tlaneops": ach, "peak_Tlaneops": peak, "frac": ach / peak,
@@ -514,7 +515,7 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": {"bf16": "bf16", "fp16": "f16", "fp32": "f32"}[args.precision],
+            "scaling": "weak", "vs_baseline": None, "dtype": {"bf16": "bf16", "fp16": "f16", "fp32": "f32", "fp32tc": "f32 (3 x bf16 tensor-core passes)"}[args.precision],
             "data": "synthetic",
             "config": {"workload": f"cfg2: BigVGAN2 decode batch {B} x {args.seconds:g} s synthetic latents per GPU "
                                    f"(T={T} frames, {B * T * HOP} samples), random-init weights of checkpoints/config.yaml",
@@ -568,7 +569,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp16", "fp32"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp16", "fp32", "fp32tc"])
     ap.add_argument("--batch", type=int, default=CFG2_B)
     ap.add_argument("--seconds", type=float, default=CFG2_SEC)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -127,12 +127,18 @@ class _AMPBlock1(nn.Module):
 
 
 class BigVGAN(nn.Module):
-    PRECISIONS = ("auto", "fp32", "fp16", "bf16")
+    PRECISIONS = ("auto", "fp32", "fp32tc", "fp16", "bf16")
+    # what "auto" resolves to outside autocast: the fp32 tensor-core mode (fp32 tensors, waveform within 1e-4 of the
+    # reference's fp32 output -- a tenth of the parity gate -- at 6x the speed of the CUDA-core mode); set to "fp32" for
+    # the CUDA-core parity mode (1e-5)
+    AUTO_FP32_PRECISION = "fp32tc"
 
     def __init__(self, h, use_cuda_kernel: bool = True, precision: str = "auto"):
-        """`precision`: "fp32" (parity mode, the reference's default arithmetic), "fp16" / "bf16" (tensor-core modes
-        with 16-bit storage), or "auto" (default): what the reference module would compute in at this call site --
-        fp16 / bf16 under ``torch.amp.autocast`` with that dtype (infer.py:456, :613), fp32 otherwise."""
+        """`precision`: "fp32" (parity mode, the reference's default arithmetic on CUDA cores), "fp32tc" (fp32 storage and
+        fp32-grade results with the convolutions on the tensor cores as three fp16 passes over split operands), "fp16" /
+        "bf16" (tensor-core modes with 16-bit storage), or "auto" (default): what the reference module would compute in
+        at this call site -- fp16 / bf16 under ``torch.amp.autocast`` with that dtype (infer.py:456, :613), fp32
+        otherwise (``AUTO_FP32_PRECISION``: the fp32 tensor-core mode)."""
         super().__init__()
         self.h = h
         try:
@@ -299,7 +305,7 @@ class BigVGAN(nn.Module):
     def activation_kernel_name(self) -> str:
         """Which Activation1d kernel bvg_forward launches in the current precision mode (for bench reports)."""
         import os
-        if self.resolved_precision() == "fp32":
+        if self.resolved_precision() in ("fp32", "fp32tc"):
             return "act1d_c8_v3_kernel (Activation1d, register-streamed fp32)"
         if os.environ.get("BVG_ACT_MMA", "1") == "0":
             return "act1d_c8_v3_kernel (Activation1d, register-streamed, packed f32x2)"
@@ -315,13 +321,14 @@ class BigVGAN(nn.Module):
             raise _lib.BvgError(f"precision must be one of {self.PRECISIONS}, got {p!r}")
         if p != "auto":
             return p
-        if torch.is_autocast_enabled():
-            dt = torch.get_autocast_gpu_dtype()
-            return "fp16" if dt == torch.float16 else ("bf16" if dt == torch.bfloat16 else "fp32")
-        return "fp32"
+        if torch.is_autocast_enabled("cuda"):
+            dt = torch.get_autocast_dtype("cuda")
+            return "fp16" if dt == torch.float16 else ("bf16" if dt == torch.bfloat16 else self.AUTO_FP32_PRECISION)
+        return self.AUTO_FP32_PRECISION
 
     def _mode(self) -> int:
-        return {"fp32": _lib.MODE_FP32, "bf16": _lib.MODE_BF16, "fp16": _lib.MODE_F16}[self.resolved_precision()]
+        return {"fp32": _lib.MODE_FP32, "bf16": _lib.MODE_BF16, "fp16": _lib.MODE_F16,
+                "fp32tc": _lib.MODE_FP32_TC}[self.resolved_precision()]
 
     def num_launches(self, frames: Sequence[int]) -> int:
         return int(self._libh.bvg_plan_num_launches(self._plan(tuple(int(f) for f in frames), self._mode())))

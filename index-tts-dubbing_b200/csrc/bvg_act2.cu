@@ -62,11 +62,35 @@ template <> struct RowOps<float> {
 // s = u + sin^2(alpha u) / (beta + 1e-9).  Fast form: sin^2 z = (1 - cos 2z)/2, so
 // s = u + h - h cos(2 alpha u) with h = inv_beta/2; the constant h is added once per OUTPUT instead
 // (the down-FIR taps sum to 1 and replicate padding passes constants through).
-template <bool PRECISE>
+template <int PRECISE>
 __device__ __forceinline__ float snake1(float u, float a, float ib_or_h) {
-  if (PRECISE) {
+  if (PRECISE == 1) {
     float sn = sinf(a * u);
     return fmaf(ib_or_h * sn, sn, u);
+  } else if (PRECISE == 2) {
+    // fast form with an fp32-grade cosine: z = k pi + r, |r| <= pi/2 (two-constant Cody-Waite, exact for |z| < 2^12 pi),
+    // cos z = (-1)^k cos r, cos r by its degree-12 even Taylor polynomial (truncation error 7e-9 at r = pi/2)
+    const float z = a * u;
+    const float k = rintf(z * 0.318309886183790672f);
+    float r = fmaf(k, -3.140625f, z);
+    r = fmaf(k, -9.67653589793e-4f, r);
+    const float r2 = r * r;
+    float c = fmaf(r2, 2.08767569878681e-9f, -2.75573192239859e-7f);
+    c = fmaf(c, r2, 2.48015873015873e-5f);
+    c = fmaf(c, r2, -1.38888888888889e-3f);
+    c = fmaf(c, r2, 4.16666666666667e-2f);
+    c = fmaf(c, r2, -0.5f);
+    c = fmaf(c, r2, 1.f);
+    c = __int_as_float(__float_as_int(c) ^ (__float2int_rn(k) << 31));
+    return fmaf(-ib_or_h, c, u);             // a = 2 alpha, ib_or_h = h
+  } else if (PRECISE == 3) {
+    // fast form, MUFU cosine of the argument reduced to [-pi, pi] (two-constant Cody-Waite): the hardware's 2^-21.2
+    // absolute error bound holds whatever the size of alpha * u
+    const float z = a * u;
+    const float k = rintf(z * 0.159154943091895336f);
+    float r = fmaf(k, -6.28125f, z);
+    r = fmaf(k, -1.935307179586e-3f, r);
+    return fmaf(-ib_or_h, __cosf(r), u);
   } else {
     return fmaf(-ib_or_h, __cosf(a * u), u);   // a = 2 alpha, ib_or_h = h
   }
@@ -77,7 +101,7 @@ constexpr float G0 = 2.f * BVG_F0, G1 = 2.f * BVG_F1, G2 = 2.f * BVG_F2, G3 = 2.
 
 // Exact output t of this thread (rows relative to r0) with both replicate paddings, reading the raw
 // rows from the thread's staging region (row index of x[j] is j - r0 + 5; staged rows are clamped).
-template <typename T, int NX, bool PRECISE>
+template <typename T, int NX, int PRECISE>
 __device__ __noinline__ float2 exact_output(const T* xr, int r0, int t, int L, float a0, float a1, float h0, float h1) {
   float accx = 0.f, accy = 0.f;
 #pragma unroll 1
@@ -99,7 +123,7 @@ __device__ __noinline__ float2 exact_output(const T* xr, int r0, int t, int L, f
     accx = fmaf(c_taps[k], snake1<PRECISE>(ux, a0, h0), accx);
     accy = fmaf(c_taps[k], snake1<PRECISE>(uy, a1, h1), accy);
   }
-  if (!PRECISE) { accx += h0; accy += h1; }
+  if (PRECISE != 1) { accx += h0; accy += h1; }
   return make_float2(accx, accy);
 }
 
@@ -130,7 +154,9 @@ __device__ __forceinline__ u64 add2(u64 a, u64 b) {
   return d;
 }
 
-template <typename T, int RT, int WPB, bool PRECISE, bool PACKED, int MINB = (sizeof(T) == 2 ? 2 : 1)>
+// SPLIT (fp32 only): the result is written as a split fp16 tensor [2 C/8][R][8] = [hi chunks | lo chunks] (split_f32 in
+// bvg_common.cuh), the A operand of the fp32 tensor-core convolutions (bvg_conv_umma.cu, F32IO), instead of fp32 rows.
+template <typename T, int RT, int WPB, int PRECISE, bool PACKED, int MINB = (sizeof(T) == 2 ? 2 : 1), bool SPLIT = false>
 __global__ void __launch_bounds__(WPB * 32, MINB)
 act1d_c8_v3_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __restrict__ alpha,
                    const float* __restrict__ inv_beta, const SegDesc* __restrict__ seg, int R, int tiles, int nchunks) {
@@ -167,7 +193,7 @@ act1d_c8_v3_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __re
   T* xr = region + (tb * RS) * 8 + 2 * cp;   // row n, this thread's channel pair: xr[n*8], xr[n*8+1]
   const int ch = chunk * 8 + 2 * cp;
   float a0 = alpha[ch], a1 = alpha[ch + 1], h0 = inv_beta[ch], h1 = inv_beta[ch + 1];
-  if (!PRECISE) { a0 *= 2.f; a1 *= 2.f; h0 *= 0.5f; h1 *= 0.5f; }
+  if (PRECISE != 1) { a0 *= 2.f; a1 *= 2.f; h0 *= 0.5f; h1 *= 0.5f; }
   cp_async_wait_all();
   __syncwarp();
 
@@ -268,7 +294,7 @@ act1d_c8_v3_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __re
       acc.x = fmaf(BVG_F3, s[2 * t + 3].x + s[2 * t + 8].x, acc.x); acc.y = fmaf(BVG_F3, s[2 * t + 3].y + s[2 * t + 8].y, acc.y);
       acc.x = fmaf(BVG_F4, s[2 * t + 4].x + s[2 * t + 7].x, acc.x); acc.y = fmaf(BVG_F4, s[2 * t + 4].y + s[2 * t + 7].y, acc.y);
       acc.x = fmaf(BVG_F5, s[2 * t + 5].x + s[2 * t + 6].x, acc.x); acc.y = fmaf(BVG_F5, s[2 * t + 5].y + s[2 * t + 6].y, acc.y);
-      if (!PRECISE) { acc.x += h0; acc.y += h1; }
+      if (PRECISE != 1) { acc.x += h0; acc.y += h1; }
       RowOps<T>::stpair(xr + t * 8, acc);   // row t is dead: in-place, own column only
     }
     }
@@ -288,18 +314,30 @@ act1d_c8_v3_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __re
     const int idx = lane + 32 * it;
     const int tb2 = idx / RT, t = idx - tb2 * RT;
     const int row = tile0 + tb2 * RT + t;
-    if (row < L) RowOps<T>::copy_row(yb + (size_t)row * 8, region + (tb2 * RS + t) * 8);
+    if (row < L) {
+      if constexpr (SPLIT) {
+        const float* src = reinterpret_cast<const float*>(region + (tb2 * RS + t) * 8);
+        Vec8<__half> hi, lo;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) split_f32(src[c], hi.v[c], lo.v[c]);
+        __half* ys = reinterpret_cast<__half*>(y);
+        hi.store(ys + ((size_t)chunk * R + sd.off + row) * 8);
+        lo.store(ys + ((size_t)(nchunks + chunk) * R + sd.off + row) * 8);
+      } else {
+        RowOps<T>::copy_row(yb + (size_t)row * 8, region + (tb2 * RS + t) * 8);
+      }
+    }
   }
 }
 
-template <typename T, int RT, int WPB, bool PRECISE, bool PACKED = false, int MINB = (sizeof(T) == 2 ? 2 : 1)>
+template <typename T, int RT, int WPB, int PRECISE, bool PACKED = false, int MINB = (sizeof(T) == 2 ? 2 : 1), bool SPLIT = false>
 cudaError_t launch_v3(const ActArgs& a, cudaStream_t s) {
   const int tiles = (a.max_len + 8 * RT - 1) / (8 * RT);
   const int nchunks = a.C / 8;
   const bool flat = tiles < 4 * WPB;   // short segments: flatten (chunk, tile) so no warp of a block idles
   dim3 grid(flat ? (tiles * nchunks + WPB - 1) / WPB : (tiles + WPB - 1) / WPB, flat ? 1 : nchunks, a.B), block(WPB * 32);
   const size_t smem = (size_t)WPB * 8 * (RT + 11) * 8 * sizeof(T);
-  auto kern = act1d_c8_v3_kernel<T, RT, WPB, PRECISE, PACKED, MINB>;
+  auto kern = act1d_c8_v3_kernel<T, RT, WPB, PRECISE, PACKED, MINB, SPLIT>;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -313,8 +351,31 @@ cudaError_t launch_v3(const ActArgs& a, cudaStream_t s) {
 cudaError_t launch_act_c8_v2(const ActArgs& a, int dtype, bool precise, int rt, cudaStream_t s) {
   if (a.B <= 0 || a.max_len <= 0) return cudaSuccess;
   if (dtype == 0) {
+    if (a.split_out || a.fast_fp32) {
+      // fp32 tensor-core mode: the fast form of SnakeBeta, s = u + h - h cos(2 alpha u), with the MUFU cosine of the
+      // Cody-Waite-reduced argument.  Measured on cfg2 (109 launches, profiles/r2g_fp32tc.md): sinf 44.9 ms, polynomial
+      // cosine 26.2 ms, plain MUFU 18.0 ms -- and the waveform error is the same 8.8e-5 for all of them (the tensor core's
+      // accumulator truncation dominates).  BVG_TC32_ACT = 1 sinf, 2 polynomial, 0 unreduced MUFU select the others.
+      static const int sel = [] { const char* e = getenv("BVG_TC32_ACT"); return e ? atoi(e) : 3; }();
+      if (!precise) return cudaErrorInvalidValue;
+      if (a.split_out) {
+        switch (sel) {
+          case 0: return launch_v3<float, 16, 4, 0, false, 1, true>(a, s);
+          case 1: return launch_v3<float, 16, 4, 1, false, 1, true>(a, s);
+          case 2: return launch_v3<float, 16, 4, 2, false, 1, true>(a, s);
+          default: return launch_v3<float, 16, 4, 3, false, 1, true>(a, s);
+        }
+      }
+      switch (sel) {
+        case 0: return launch_v3<float, 16, 4, 0>(a, s);
+        case 1: return launch_v3<float, 16, 4, 1>(a, s);
+        case 2: return launch_v3<float, 16, 4, 2>(a, s);
+        default: return launch_v3<float, 16, 4, 3>(a, s);
+      }
+    }
     return precise ? launch_v3<float, 16, 4, true>(a, s) : launch_v3<float, 16, 4, false>(a, s);
   }
+  if (a.split_out) return cudaErrorInvalidValue;
   if (precise) return launch_v3<__nv_bfloat16, 16, 8, true>(a, s);
   static const int packed = [] { const char* e = getenv("BVG_ACT_PACKED"); return e ? atoi(e) : 1; }();
   if (packed) {

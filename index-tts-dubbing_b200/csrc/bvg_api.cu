@@ -61,6 +61,8 @@ struct ConvLayer {
   const float* fold_res = nullptr;   // [Cout] factor on the residual input (the residual stream is stored pre-scaled)
   float* fold_buf = nullptr;         // device storage owned by this layer for fold_out / fold_res products ([2 * Cout])
   bool k_packed = false;             // the UMMA images are K-packed (24-channel layers, bvg_conv_umma.cu)
+  void* w_umma3 = nullptr;           // fp32 tensor-core mode: fp16 image of S [W_hi; 2^-11 W_hi; W_lo] (3 Cin input channels), built on first use
+  float tc32_acc_scale = 1.f;        // 1 / S
   void setup() {
     if (!transposed) {
       ntaps = k; N = Cout; u = 1; p = 0; q_extra = 0;
@@ -127,6 +129,7 @@ struct bvg_handle {
   int64_t plans_created = 0;
   int num_sms = 148;
   bool finalized = false;
+  bool tc32_ready = false;  // the w_umma3 images exist (BVG_MODE_FP32_TC, built by the first forward that needs them)
   int launch_counter = 0;   // kernel launches issued by the forward in progress
   // optional per-launch CUDA-event timing (bench.py's roofline numbers)
   bool prof_on = false;
@@ -175,7 +178,7 @@ struct bvg_plan {
   bool tab_uploaded = false;    // the first forward copies the slice to the device on ITS stream
   std::vector<int> total_mt;    // [g][msub in 1,2,4][q_extra]
   size_t ws_bytes = 0;
-  size_t off_lat = 0, off_pre = 0, off_bias = 0;
+  size_t off_lat = 0, off_pre = 0, off_bias = 0, off_split0 = 0;
   std::vector<size_t> off_U, off_X, off_A, off_Y, off_XS;
   int bias_stride = 0;
   std::vector<int> bias_off;    // per cond layer (0 = pre, 1.. = ups)
@@ -266,7 +269,24 @@ int run_conv(const ConvLayer& L, const bvg_plan* p, int gin, int gout, const voi
   // algorithmic work of this launch: 2 * Cin * taps * N MACs per input row (valid rows only)
   const double flops = 2.0 * L.Cin * L.ntaps * L.N * (double)p->sumlen[gin];
   const double bytes = ((double)L.Cin * p->sumlen[gin] + (double)L.Cout * p->sumlen[gout] * (res ? 2 : 1)) * p->esize;
-  if (p->mode != BVG_MODE_FP32 && L.w_umma) {
+  if (p->mode == BVG_MODE_FP32_TC) {
+    // x is the split [hi | lo] fp16 view of the fp32 input; the GEMM runs over 3 Cin channels (lo, hi, hi again)
+    // against S [2^-11 W_hi; W_lo; W_hi]; bias / residual / old output / store in fp32 (three tensor-core passes per MAC)
+    if (!L.w_umma3) return fail("fp32 tensor-core mode: layer without a split weight image (Cin %d, N %d)", L.Cin, L.N);
+    ConvArgs a = make_conv_args(L, p, gin, gout, x, y, res, bias, bias_bstride, scale, accumulate, false);
+    a.w = L.w_umma3; a.dtype = 2; a.f32io = 1; a.split3_chunks = L.Cin / 8; a.Cin = 3 * L.Cin;
+    a.acc_scale = L.tc32_acc_scale;
+    a.msub = conv_umma_default_msub(a);
+    const int ti = (gin * 3 + (a.msub == 4 ? 2 : a.msub - 1)) * 2 + (L.q_extra ? 1 : 0);
+    a.tile_prefix = p->prefix_dev + (size_t)ti * (p->B + 1);
+    a.total_mt = p->total_mt[ti];
+    if (!conv_umma_supported(a)) return fail("fp32 tensor-core mode: layer shape not supported (Cin %d, N %d)", L.Cin, L.N);
+    ProfScope ps(p->h, s, PROF_CONV_TC, flops, bytes);   // algorithmic flops (the tensor cores do 3x that)
+    CK(launch_conv_umma(a, s));
+    ++p->h->launch_counter;
+    return 0;
+  }
+  if (p->mode != BVG_MODE_FP32 && L.w_umma) {   // (BVG_MODE_FP32_TC returned above)
     const float* ubias = (L.bias_umma && bias == L.bias) ? L.bias_umma : bias;   // the image's output channels are pre-scaled
     ConvArgs a = make_conv_args(L, p, gin, gout, x, y, res, ubias, bias_bstride, scale, accumulate, true);
     if (conv_umma_supported(a)) {
@@ -283,7 +303,7 @@ int run_conv(const ConvLayer& L, const bvg_plan* p, int gin, int gout, const voi
   return 0;
 }
 
-int run_act(const ActLayer& A, const bvg_plan* p, int g, const void* x, void* y, cudaStream_t s);
+int run_act(const ActLayer& A, const bvg_plan* p, int g, const void* x, void* y, cudaStream_t s, bool split_out = false);
 
 // Activation1d followed by a convolution (one step of AMPBlock1.forward, models.py:69-72).  In the bf16
 // mode the activation is fused into the conv kernel's producer stage when the layer allows it (the whole
@@ -301,18 +321,62 @@ int run_act_conv(const ActLayer& A, const ConvLayer& L, const bvg_plan* p, int g
       return 0;
     }
   }
-  if (run_act(A, p, g, raw, actbuf, s)) return 1;
+  if (run_act(A, p, g, raw, actbuf, s, p->mode == BVG_MODE_FP32_TC)) return 1;
   return run_conv(L, p, g, g, actbuf, y, res, L.bias, 0, scale, accumulate, s);
 }
 
-int run_act(const ActLayer& A, const bvg_plan* p, int g, const void* x, void* y, cudaStream_t s) {
+int run_act(const ActLayer& A, const bvg_plan* p, int g, const void* x, void* y, cudaStream_t s, bool split_out) {
   ActArgs aa{x, y, A.alpha, A.inv_beta, p->seg_dev + (size_t)g * p->B, p->R[g], p->C[g], p->B, p->maxlen[g]};
-  aa.prescaled = (A.prescaled && p->mode != BVG_MODE_FP32) ? 1 : 0;
+  const bool f32 = p->mode == BVG_MODE_FP32 || p->mode == BVG_MODE_FP32_TC;
+  aa.prescaled = (A.prescaled && !f32) ? 1 : 0;
+  aa.split_out = split_out ? 1 : 0;
+  aa.fast_fp32 = p->mode == BVG_MODE_FP32_TC ? 1 : 0;
   // algorithmic bytes of a standalone Activation1d launch: read + write of every valid element
   const double bytes = 2.0 * p->C[g] * (double)p->sumlen[g] * p->esize;
   ProfScope ps(p->h, s, PROF_ACT, 0.0, bytes);
-  CK(launch_act_c8(aa, p->dtype, p->mode == BVG_MODE_FP32, s));
+  CK(launch_act_c8(aa, p->dtype, f32, s));
   ++p->h->launch_counter;
+  return 0;
+}
+
+// BVG_MODE_FP32_TC: the S [W_hi; 2^-11 W_hi; W_lo] images of every convolution on the path, built once per handle on the
+// stream of the first forward that needs them (the 16-bit modes never pay for them: + 3x the fp16 weights = 0.68 GB).
+int build_tc32_image(bvg_handle* h, ConvLayer& L, float* w3, float absmax, cudaStream_t s) {
+  const size_t bytes = umma_weight_image_bytes(L.ntaps, 3 * L.Cin, L.N);
+  if (!bytes) return fail("fp32 tensor-core mode: no tiling for Cin %d, N %d", L.Cin, L.N);
+  if (!L.w_umma3 && dev_alloc(h, &L.w_umma3, bytes)) return 1;
+  const float S = split3_weight_scale(absmax);
+  L.tc32_acc_scale = 1.f / S;
+  CK(launch_split3_weights(L.w_tap, w3, L.ntaps, L.Cin, L.N, S, s));
+  CK(launch_repack_umma(w3, L.w_umma3, 2, L.ntaps, 3 * L.Cin, L.N, 1.f, false, s));
+  return 0;
+}
+
+int ensure_tc32_images(bvg_handle* h, cudaStream_t s) {
+  if (h->tc32_ready) return 0;
+  std::vector<ConvLayer*> layers{&h->conv_pre};
+  for (auto& L : h->ups) layers.push_back(&L);
+  for (auto& L : h->c1) layers.push_back(&L);
+  for (auto& L : h->c2) layers.push_back(&L);
+  size_t mx = 0;
+  for (ConvLayer* L : layers) mx = std::max(mx, (size_t)L->Cin * L->Cout * L->k);
+  float *w3 = nullptr, *amax = nullptr;
+  std::vector<float> amax_h(layers.size());
+  CK(cudaMalloc((void**)&amax, layers.size() * sizeof(float)));
+  if (cudaMalloc((void**)&w3, 3 * mx * sizeof(float)) != cudaSuccess) { cudaFree(amax); return fail("fp32 tensor-core mode: scratch allocation failed"); }
+  int rc = 0;
+  auto ck = [&](cudaError_t e) { if (e != cudaSuccess && !rc) rc = fail("fp32 tensor-core images: %s", cudaGetErrorString(e)); };
+  ck(cudaMemsetAsync(amax, 0, layers.size() * sizeof(float), s));
+  for (size_t i = 0; i < layers.size() && !rc; ++i)
+    ck(launch_absmax(layers[i]->w_tap, (size_t)layers[i]->Cin * layers[i]->Cout * layers[i]->k, amax + i, s));
+  ck(cudaMemcpyAsync(amax_h.data(), amax, layers.size() * sizeof(float), cudaMemcpyDeviceToHost, s));
+  ck(cudaStreamSynchronize(s));
+  for (size_t i = 0; i < layers.size() && !rc; ++i) rc = build_tc32_image(h, *layers[i], w3, amax_h[i], s);
+  cudaStreamSynchronize(s);
+  cudaFree(w3);
+  cudaFree(amax);
+  if (rc) return 1;
+  h->tc32_ready = true;
   return 0;
 }
 
@@ -681,12 +745,13 @@ int bvg_speaker_embedding(bvg_handle* h, const float* mel, int32_t B, int32_t Tm
 
 int bvg_plan_create(bvg_handle* h, int32_t B, const int32_t* frames, int32_t mode, bvg_plan** out) {
   if (!h || !frames || !out || B < 1) return fail("bvg_plan_create: bad argument");
-  if (mode != BVG_MODE_FP32 && mode != BVG_MODE_BF16 && mode != BVG_MODE_F16) return fail("bvg_plan_create: unknown mode %d", mode);
+  if (mode != BVG_MODE_FP32 && mode != BVG_MODE_BF16 && mode != BVG_MODE_F16 && mode != BVG_MODE_FP32_TC)
+    return fail("bvg_plan_create: unknown mode %d", mode);
   static uint64_t next_uid = 1;
   bvg_plan* p = new bvg_plan();
   p->uid = next_uid++;
   p->h = h; p->B = B; p->mode = mode;
-  p->dtype = mode == BVG_MODE_FP32 ? 0 : (mode == BVG_MODE_BF16 ? 1 : 2);   // storage type of the packed tensors
+  p->dtype = (mode == BVG_MODE_FP32 || mode == BVG_MODE_FP32_TC) ? 0 : (mode == BVG_MODE_BF16 ? 1 : 2);   // storage type of the packed tensors
   p->esize = p->dtype == 0 ? 4 : 2;
   p->frames.assign(frames, frames + B);
   const int ng = h->nups + 1;
@@ -749,6 +814,9 @@ int bvg_plan_create(bvg_handle* h, int32_t B, const int32_t* frames, int32_t mod
   const size_t es = p->esize;
   p->off_lat = take((size_t)h->cfg.gpt_dim * p->R[0] * es);
   p->off_pre = take((size_t)p->C[0] * p->R[0] * es);
+  // fp32 tensor-core mode: the split [hi | lo] copy of conv_pre's output, input of the first up-convolution (the later
+  // stages split their input into the previous stage's activation buffer, which is free by then)
+  p->off_split0 = mode == BVG_MODE_FP32_TC ? take((size_t)p->C[0] * p->R[0] * es) : 0;
   p->off_U.resize(ng); p->off_X.resize(ng); p->off_A.resize(ng); p->off_Y.resize(ng); p->off_XS.resize(ng);
   for (int g = 1; g < ng; ++g) {
     size_t bytes = (size_t)p->C[g] * p->R[g] * es;
@@ -814,6 +882,8 @@ static int forward_impl(bvg_handle* h, bvg_plan* p, const void* latent, int32_t 
   cudaStream_t s = (cudaStream_t)stream;
   char* ws = (char*)workspace;
   const int B = p->B, ng = h->nups + 1, dt = p->dtype;
+  const bool tc32 = p->mode == BVG_MODE_FP32_TC;
+  if (tc32 && ensure_tc32_images(h, s)) return 1;
   // plan tables: pinned host mirror -> device slice, once, ordered on this stream (no allocation, no host sync)
   if (!p->tab_uploaded) {
     CK(cudaMemcpyAsync(p->tab_dev, p->tab_host, p->tab_bytes, cudaMemcpyHostToDevice, s));
@@ -824,13 +894,18 @@ static int forward_impl(bvg_handle* h, bvg_plan* p, const void* latent, int32_t 
   // 2 + 5 * nups buffers on every forward (a few hundred KB of stores).
   {
     GuardJobs jobs{};
-    auto add = [&](size_t off, int g, int C) {
-      jobs.job[jobs.n++] = GuardJob{ws + off, p->seg_dev + (size_t)g * B, C >> 3, p->R[g], p->esize == 4 ? 2 : 1};
+    auto add = [&](size_t off, int g, int C, bool split = false) {
+      // (a split buffer is a bf16 tensor of 2 C channels in the same bytes)
+      if (split) jobs.job[jobs.n++] = GuardJob{ws + off, p->seg_dev + (size_t)g * B, 2 * (C >> 3), p->R[g], 1};
+      else jobs.job[jobs.n++] = GuardJob{ws + off, p->seg_dev + (size_t)g * B, C >> 3, p->R[g], p->esize == 4 ? 2 : 1};
     };
-    add(p->off_lat, 0, h->cfg.gpt_dim);
+    add(p->off_lat, 0, h->cfg.gpt_dim, tc32);
     add(p->off_pre, 0, p->C[0]);
-    for (int g = 1; g < ng; ++g)
-      for (size_t o : {p->off_U[g], p->off_X[g], p->off_A[g], p->off_Y[g], p->off_XS[g]}) add(o, g, p->C[g]);
+    if (tc32) add(p->off_split0, 0, p->C[0], true);
+    for (int g = 1; g < ng; ++g) {
+      for (size_t o : {p->off_U[g], p->off_X[g], p->off_Y[g], p->off_XS[g]}) add(o, g, p->C[g]);
+      add(p->off_A[g], g, p->C[g], tc32);
+    }
     ProfScope ps(h, s, PROF_OTHER, 0.0, 0.0);
     CK(launch_zero_guards_all(jobs, B, s));
   }
@@ -840,7 +915,7 @@ static int forward_impl(bvg_handle* h, bvg_plan* p, const void* latent, int32_t 
   const int D = h->cfg.speaker_embedding_dim;
   {
   ProfScope ps(h, s, PROF_OTHER, 0.0, (double)h->cfg.gpt_dim * p->sumlen[0] * (4.0 + p->esize));
-  CK(launch_pack_latent(latent, latent_dtype, ws + p->off_lat, dt, seg0, ragged ? p->latrow_dev : nullptr, B, p->max_frames,
+  CK(launch_pack_latent(latent, latent_dtype, ws + p->off_lat, tc32 ? 3 : dt, seg0, ragged ? p->latrow_dev : nullptr, B, p->max_frames,
                         h->cfg.gpt_dim, p->R[0], s));
   // speaker conditioning folded into per-segment biases
   CK(launch_cond_bias(h->conv_pre.bias, h->cond_pre.w, h->cond_pre.b, spk_emb, biasb + p->bias_off[0], p->C[0], D, B,
@@ -860,6 +935,13 @@ static int forward_impl(bvg_handle* h, bvg_plan* p, const void* latent, int32_t 
     char *U = ws + p->off_U[g], *X = ws + p->off_X[g], *A = ws + p->off_A[g], *Y = ws + p->off_Y[g],
          *XS = ws + p->off_XS[g];
     // up-convolution + conditioning (models.py:230-234)
+    if (tc32) {   // split the fp32 stage input for the tensor cores
+      char* sp = g == 1 ? ws + p->off_split0 : ws + p->off_A[g - 1];
+      ProfScope ps(h, s, PROF_OTHER, 0.0, 2.0 * p->C[g - 1] * (double)p->sumlen[g - 1] * 4.0);
+      CK(launch_split_c8((const float*)stage_in, sp, p->seg_dev + (size_t)(g - 1) * B, B, p->C[g - 1], p->R[g - 1], p->maxlen[g - 1], s));
+      ++h->launch_counter;
+      stage_in = sp;
+    }
     if (run_conv(h->ups[i], p, g - 1, g, stage_in, U, nullptr, biasb + p->bias_off[g], p->bias_stride, 1.f, 0, s))
       return 1;
     for (int j = 0; j < h->nk; ++j) {          // AMP blocks (models.py:237-243)
@@ -882,9 +964,11 @@ static int forward_impl(bvg_handle* h, bvg_plan* p, const void* latent, int32_t 
   {
     const int g = ng - 1;
     const SegDesc* seg = p->seg_dev + (size_t)g * B;
-    if (run_act(h->act_post, p, g, stage_in, ws + p->off_A[g], s)) return 1;
+    // (fp32 tensor-core mode: A[g] holds split data and split-view guard rows; the plain fp32 result goes to Y[g])
+    char* post = tc32 ? ws + p->off_Y[g] : ws + p->off_A[g];
+    if (run_act(h->act_post, p, g, stage_in, post, s)) return 1;
     ProfScope ps(h, s, PROF_OTHER, 0.0, ((double)p->C[g] * p->esize + 4.0) * (double)p->sumlen[g]);
-    CK(launch_conv_post_tanh(ws + p->off_A[g], dt, h->conv_post.w_raw, h->conv_post.bias, wav, (short*)pcm, seg,
+    CK(launch_conv_post_tanh(post, dt, h->conv_post.w_raw, h->conv_post.bias, wav, (short*)pcm, seg,
                              ragged ? p->latrow_dev : nullptr, h->hop, B, p->C[g], p->R[g], p->max_frames * h->hop, s));
   }
   p->num_launches = h->launch_counter;   // what this forward actually issued (fused layers launch once)
@@ -1030,13 +1114,19 @@ int conv_op(bool transposed, const float* x, const float* w, const float* bias, 
     }
   }
   if (tc32) {
-    // [hi | lo] split of the fp32 input, [W_hi; W_hi; W_lo] weight image, fp32 epilogue
-    void* xs; float* w3;
-    if (tmp.alloc(&xs, (size_t)Cin * Rin * 4) || tmp.alloc((void**)&w3, 3 * (size_t)Cin * Cout * k * sizeof(float))) return 1;
+    // [hi | lo] fp16 split of the fp32 input, S [W_hi; 2^-11 W_hi; W_lo] weight image, fp32 epilogue
+    void* xs; float *w3, *amax, amax_h = 0.f;
+    if (tmp.alloc(&xs, (size_t)Cin * Rin * 4) || tmp.alloc((void**)&w3, 3 * (size_t)Cin * Cout * k * sizeof(float)) ||
+        tmp.alloc((void**)&amax, sizeof(float))) return 1;
     CK(cudaMemsetAsync(xs, 0, (size_t)Cin * Rin * 4, s));
+    CK(cudaMemsetAsync(amax, 0, sizeof(float), s));
     CK(launch_split_c8((const float*)a.x, xs, seg_dev, B, Cin, Rin, T, s));
-    CK(launch_split3_weights(wt, w3, L.ntaps, Cin, L.N, s));
-    a.x = xs; a.dtype = 1; a.f32io = 1; a.split3_chunks = Cin / 8; a.Cin = 3 * Cin;
+    CK(launch_absmax(wt, (size_t)Cin * Cout * k, amax, s));
+    CK(cudaMemcpyAsync(&amax_h, amax, sizeof(float), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    const float S = split3_weight_scale(amax_h);
+    CK(launch_split3_weights(wt, w3, L.ntaps, Cin, L.N, S, s));
+    a.x = xs; a.dtype = 2; a.f32io = 1; a.split3_chunks = Cin / 8; a.Cin = 3 * Cin; a.acc_scale = 1.f / S;
     a.msub = conv_umma_default_msub(a);
     std::vector<int> pf(B + 1, 0);
     for (int b = 0; b < B; ++b) pf[b + 1] = pf[b] + (T + L.q_extra + 128 * a.msub - 1) / (128 * a.msub);
@@ -1048,7 +1138,7 @@ int conv_op(bool transposed, const float* x, const float* w, const float* bias, 
     size_t bytes = umma_weight_image_bytes(L.ntaps, 3 * Cin, L.N);
     if (!bytes || !conv_umma_supported(a)) return fail("conv op: shape not supported by the tcgen05 kernel (fp32 tensor-core mode)");
     if (tmp.alloc(&wu, bytes)) return 1;
-    CK(launch_repack_umma(w3, wu, 1, L.ntaps, 3 * Cin, L.N, 1.f, false, s));
+    CK(launch_repack_umma(w3, wu, 2, L.ntaps, 3 * Cin, L.N, 1.f, false, s));
     a.w = wu;
     CK(launch_conv_umma(a, s));
   } else if (mode != BVG_MODE_FP32) {

@@ -55,9 +55,11 @@ struct ConvArgs {
   int msub;                 // 1, 2 or 4
   int bn_small;             // 1: `w` is the 64-column n-tile image (small-batch variant of a wide layer), msub must be 1
   int k_packed;             // 1: `w` is the K-packed image of a 24-channel layer (taps share K-steps, see make_tiling)
-  // fp32 tensor-core mode (bvg_conv_umma.cu, F32IO): x is a SPLIT tensor -- split3_chunks 8-channel chunks of bf16 "hi"
-  // values followed by as many chunks of bf16 "lo" residuals (x ~ hi + lo to 16 bits) -- and Cin counts 3 x the real input
-  // channels: the GEMM multiplies [hi | lo | hi] with the weight image [W_hi; W_hi; W_lo]; y / res are fp32 packed tensors
+  // fp32 tensor-core mode (bvg_conv_umma.cu, F32IO): x is a SPLIT tensor -- split3_chunks 8-channel chunks of fp16 "hi"
+  // values followed by as many chunks of fp16 remainders 2^11 (x - hi) (22 significand bits together, split_f32 below) --
+  // and Cin counts 3 x the real input channels: the GEMM multiplies [lo | hi | hi] with the fp16 weight image
+  // S [2^-11 W_hi; W_lo; W_hi] (S = the layer's power-of-two scale, acc_scale = 1 / S); y / res are fp32 packed tensors
+  float acc_scale;   // f32io: factor on the accumulator (undoes the power-of-two scale of the fp16 weight image)
   int f32io;
   int split3_chunks;
   // fused Activation1d (tcgen05 kernel, bf16): when set, x is the RAW input and the kernel applies the
@@ -76,6 +78,8 @@ struct ActArgs {
   // 16-bit tensor-core kernel only: x holds 2*alpha*x_true per channel (folded into the producing convolution's weights)
   // and y receives 2*alpha*y_true (unfolded by the consuming convolution's weights): saves the per-sample argument multiply
   int prescaled;
+  int fast_fp32;   // fp32 kernel only: fp32 tensor-core mode's activation arithmetic (see launch_act_c8_v2)
+  int split_out;   // fp32 kernel only: y is a split bf16 tensor [hi chunks | lo chunks] (fp32 tensor-core mode)
 };
 
 // -------------------------------------------------------------------------------------------
@@ -124,6 +128,20 @@ template <> struct Vec8<__half> {
     *reinterpret_cast<uint4*>(p) = r;
   }
 };
+
+// fp32 tensor-core mode: x = hi + lo with hi = fp16(x) (saturating) and the remainder kept as fp16(2^11 (x - hi)) -- 22
+// significand bits in two fp16 numbers; the 2^11 keeps the remainder out of fp16's subnormal range and is undone by the
+// weight image's second block (bvg_conv_umma.cu, split3_weights_kernel).
+constexpr float BVG_SPLIT_LO_SCALE = 2048.f;
+__device__ __forceinline__ float f16_round_sat(float v) {
+  unsigned short h;
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(h) : "f"(v));
+  return __half2float(__ushort_as_half(h));
+}
+__device__ __forceinline__ void split_f32(float v, float& hi, float& lo_scaled) {
+  hi = f16_round_sat(v);
+  lo_scaled = (v - hi) * BVG_SPLIT_LO_SCALE;   // (rounded to fp16 by the Vec8<__half> store)
+}
 
 __device__ __forceinline__ float to_f32(float x) { return x; }
 __device__ __forceinline__ float to_f32(__nv_bfloat16 x) { return __bfloat162float(x); }

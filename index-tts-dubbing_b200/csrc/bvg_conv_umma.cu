@@ -44,6 +44,7 @@
 //     idle pipe time (BVG_CONV_TRACE showed ~400 cycles per tap) -> incremental 32-bit descriptors and
 //     straight-line K-step sequences; tools/umma_bench2.cu gives the per-shape floor (46 cycles for
 //     M128 x N32 x K16: the A operand's shared-memory reads, not the math).
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <type_traits>
@@ -485,7 +486,11 @@ __global__ void __launch_bounds__(FUSE ? NTHREADS_FUSED : 64 + 32 * EPW, 1) conv
             const uint32_t adst = smem_u32(a_smem + (size_t)sa * ka.a_stage_bytes);
             for (int c = 0; c < kcl; ++c) {
               int cc = kb * ka.KC + c;
-              if (F32IO && cc >= 2 * a.split3_chunks) cc -= 2 * a.split3_chunks;   // third block of the split GEMM = the hi chunks again
+              if (F32IO) {
+                // GEMM channel blocks [lo | hi | hi] over the tensor's [hi | lo] chunks (the small terms accumulate first)
+                const int c8 = a.split3_chunks;
+                cc = cc < c8 ? cc + c8 : (cc < 2 * c8 ? cc - c8 : cc - 2 * c8);
+              }
               const __nv_bfloat16* src = xg + ((size_t)cc * a.Rx + row0c) * 8;
               bulk_g2s(adst + (uint32_t)(c * ka.astride) * 16, src, (uint32_t)(arows * 16), A_FULL(sa));
             }
@@ -753,7 +758,7 @@ __global__ void __launch_bounds__(FUSE ? NTHREADS_FUSED : 64 + 32 * EPW, 1) conv
               const size_t off = ((size_t)(co >> 3) * a.Ry + soc.off + orow) * 8;
               float v[8];
 #pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[8 * u + j]) + (biasp ? __ldg(biasp + co + j) : 0.f);
+              for (int j = 0; j < 8; ++j) v[j] = fmaf(__uint_as_float(r[8 * u + j]), a.acc_scale, biasp ? __ldg(biasp + co + j) : 0.f);
               if (rf) {
                 const float4 r0 = *reinterpret_cast<const float4*>(rf + off), r1 = *reinterpret_cast<const float4*>(rf + off + 4);
                 v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w; v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
@@ -1244,27 +1249,39 @@ bool configure_fused(const ConvArgs& a, int msub, UmmaKernelArgs& ka, size_t& sm
 
 }  // namespace
 
-// fp32 tensor-core mode: W' [tap][3 Cin][N] = [W_hi; W_hi; W_lo] with W_hi = bf16(W), W_lo = bf16(W - W_hi) (both exactly
-// representable, so the bf16 repack that follows does not round again)
-__global__ void split3_weights_kernel(const float* __restrict__ w, float* __restrict__ w3, int ntaps, int Cin, int N) {
+// fp32 tensor-core mode: W' [tap][3 Cin][N] = [2^-11 W_hi; W_lo; W_hi] with W_hi = fp16(S W), W_lo = fp16(S W - W_hi) (all
+// exactly representable, so the fp16 repack that follows does not round again).  The kernel reads the input as the three
+// channel blocks [2^11 x_lo | x_hi | x_hi] (split_f32), so the GEMM delivers S (x_lo W_hi + x_hi W_lo + x_hi W_hi): every
+// product is exact in the fp32 accumulator and only x_lo W_lo (2^-22 relative) is dropped.  S is a power of two that puts
+// the layer's largest weight in [2^13, 2^14): W_lo then stays a normal fp16 number for weights down to 2^-13 of the largest.
+// Block order: the tensor core truncates its fp32 accumulator once per MMA (measured: 2.6e-8 x |acc| per MMA of the chain,
+// linear in the chain length), so the two correction blocks run first, while the accumulator is 2^-11 of its final size,
+// and only the W_hi x_hi third of the chain pays the truncation.
+__global__ void split3_weights_kernel(const float* __restrict__ w, float* __restrict__ w3, int ntaps, int Cin, int N, float scale) {
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t total = (size_t)ntaps * Cin * N;
   if (idx >= total) return;
   const int n = idx % N;
   size_t r = idx / N;
   const int ci = r % Cin, tap = r / Cin;
-  const float v = w[idx];
-  const float hi = __bfloat162float(__float2bfloat16_rn(v));
-  const float lo = __bfloat162float(__float2bfloat16_rn(v - hi));
+  const float v = w[idx] * scale;
+  const float hi = f16_round_sat(v);
+  const float lo = f16_round_sat(v - hi);
   float* base = w3 + (size_t)tap * 3 * Cin * N;
-  base[(size_t)ci * N + n] = hi;
-  base[(size_t)(Cin + ci) * N + n] = hi;
-  base[(size_t)(2 * Cin + ci) * N + n] = lo;
+  base[(size_t)ci * N + n] = f16_round_sat(hi * (1.f / BVG_SPLIT_LO_SCALE));
+  base[(size_t)(Cin + ci) * N + n] = lo;
+  base[(size_t)(2 * Cin + ci) * N + n] = hi;
 }
-cudaError_t launch_split3_weights(const float* w_tap_major, float* w3, int ntaps, int Cin, int N, cudaStream_t s) {
+cudaError_t launch_split3_weights(const float* w_tap_major, float* w3, int ntaps, int Cin, int N, float scale, cudaStream_t s) {
   size_t total = (size_t)ntaps * Cin * N;
-  split3_weights_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(w_tap_major, w3, ntaps, Cin, N);
+  split3_weights_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(w_tap_major, w3, ntaps, Cin, N, scale);
   return cudaGetLastError();
+}
+float split3_weight_scale(float absmax) {
+  if (!(absmax > 0.f) || !std::isfinite(absmax)) return 1.f;
+  int e = 0;
+  std::frexp(absmax, &e);               // absmax = m 2^e, m in [0.5, 1)
+  return std::ldexp(1.f, 14 - e);       // S absmax in [2^13, 2^14)
 }
 
 bool umma_k_packed_default(int Cin, int N) {
@@ -1383,7 +1400,7 @@ cudaError_t launch_conv_umma(const ConvArgs& a, cudaStream_t s) {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_umma_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_umma_kernel<false, EPIW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_umma_kernel<false, EPIW, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_umma_kernel<false, EPIW, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX);
     if (e != cudaSuccess) return e;
     sms_of_dev[dev] = n;
   }
@@ -1407,8 +1424,8 @@ cudaError_t launch_conv_umma(const ConvArgs& a, cudaStream_t s) {
   dim3 grid(total_tiles < num_sms ? total_tiles : num_sms), block(fuse ? NTHREADS_FUSED : (epiw4 ? 64 + 32 * 4 : NTHREADS));
   cudaError_t le;
   if (a.f32io) {
-    if (fuse || a.dtype != 1 || a.k_packed || a.bn_small || a.split3_chunks * 24 != a.Cin) return cudaErrorInvalidValue;
-    le = launch_pdl(conv_umma_kernel<false, EPIW, false, true>, grid, dim3(NTHREADS), smem, s, ka);
+    if (fuse || a.dtype != 2 || a.k_packed || a.bn_small || a.split3_chunks * 24 != a.Cin) return cudaErrorInvalidValue;
+    le = launch_pdl(conv_umma_kernel<false, EPIW, true, true>, grid, dim3(NTHREADS), smem, s, ka);
   }
   else if (a.dtype == 2 && !fuse) le = launch_pdl(conv_umma_kernel<false, EPIW, true>, grid, dim3(NTHREADS), smem, s, ka);
   else if (fuse) le = launch_pdl(conv_umma_kernel<true>, grid, block, smem, s, ka);

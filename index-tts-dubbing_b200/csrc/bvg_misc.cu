@@ -1,5 +1,6 @@
 // Small kernels around the convolution / activation hot ops: layout packing, weight repacking,
 // the speaker-conditioning projection folded into per-segment biases, and conv_post + tanh.
+#include <algorithm>
 #include <cstdlib>
 
 #include "bvg_common.cuh"
@@ -26,6 +27,27 @@ __global__ void pack_latent_kernel(const TI* __restrict__ x, TO* __restrict__ y,
 #pragma unroll
   for (int c = 0; c < 8; ++c) v.v[c] = to_f32(p[c]);
   v.store(y + ((size_t)chunk * R + sd.off + t) * 8);
+}
+
+// latent -> split fp16 tensor [2 C/8][R][8] = [hi | lo] (fp32 tensor-core mode)
+template <typename TI>
+__global__ void pack_latent_split_kernel(const TI* __restrict__ x, __half* __restrict__ y, const SegDesc* __restrict__ seg,
+                                         const int* __restrict__ src_row, int B, int Tmax, int C, int R) {
+  const int nch = C >> 3;
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t total = (size_t)B * Tmax * nch;
+  if (idx >= total) return;
+  int chunk = idx % nch;
+  size_t bt = idx / nch;
+  int t = bt % Tmax, b = bt / Tmax;
+  SegDesc sd = seg[b];
+  if (t >= sd.len) return;
+  const TI* p = x + ((src_row ? (size_t)src_row[b] : (size_t)b * Tmax) + t) * C + chunk * 8;
+  Vec8<__half> hi, lo;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) split_f32(to_f32(p[c]), hi.v[c], lo.v[c]);
+  hi.store(y + ((size_t)chunk * R + sd.off + t) * 8);
+  lo.store(y + ((size_t)(nch + chunk) * R + sd.off + t) * 8);
 }
 
 // fp32 [B, C, T]  <->  packed c8 (test entry points only)
@@ -175,8 +197,8 @@ __global__ void zero_guards_all_kernel(const GuardJobs jobs, int B) {
   for (int i = threadIdx.x; i < n; i += blockDim.x) p[i] = z;
 }
 
-// packed fp32 [C/8][R][8] -> split bf16 [2 C/8][R][8]: hi = bf16(x) in chunk c, lo = bf16(x - hi) in chunk C/8 + c
-__global__ void split_c8_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, const SegDesc* __restrict__ seg,
+// packed fp32 [C/8][R][8] -> split fp16 [2 C/8][R][8]: hi = fp16(x) in chunk c, 2^11 (x - hi) in chunk C/8 + c (split_f32)
+__global__ void split_c8_kernel(const float* __restrict__ x, __half* __restrict__ y, const SegDesc* __restrict__ seg,
                                 int nch, int R, int max_len) {
   const int b = blockIdx.z, chunk = blockIdx.y;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -185,12 +207,9 @@ __global__ void split_c8_kernel(const float* __restrict__ x, __nv_bfloat16* __re
   const size_t row = (size_t)chunk * R + sd.off + t;
   Vec8<float> v;
   v.load(x + row * 8);
-  Vec8<__nv_bfloat16> hi, lo;
+  Vec8<__half> hi, lo;
 #pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    hi.v[c] = __bfloat162float(__float2bfloat16_rn(v.v[c]));
-    lo.v[c] = v.v[c] - hi.v[c];
-  }
+  for (int c = 0; c < 8; ++c) split_f32(v.v[c], hi.v[c], lo.v[c]);
   hi.store(y + row * 8);
   lo.store(y + ((size_t)(nch + chunk) * R + sd.off + t) * 8);
 }
@@ -207,7 +226,21 @@ inline int nblk(size_t n, int t) { return (int)((n + t - 1) / t); }
 cudaError_t launch_split_c8(const float* x, void* y_split, const SegDesc* seg, int B, int C, int R, int max_len, cudaStream_t s) {
   if (B <= 0 || max_len <= 0) return cudaSuccess;
   dim3 grid(nblk(max_len, 256), C >> 3, B);
-  split_c8_kernel<<<grid, 256, 0, s>>>(x, (__nv_bfloat16*)y_split, seg, C >> 3, R, max_len);
+  split_c8_kernel<<<grid, 256, 0, s>>>(x, (__half*)y_split, seg, C >> 3, R, max_len);
+  return cudaGetLastError();
+}
+
+// max |x| over n floats into *out (which the caller zeroed): non-negative floats order like their bit patterns
+__global__ void absmax_kernel(const float* __restrict__ x, size_t n, unsigned* __restrict__ out) {
+  float m = 0.f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) m = fmaxf(m, fabsf(x[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out, __float_as_uint(m));
+}
+cudaError_t launch_absmax(const float* x, size_t n, float* out, cudaStream_t s) {
+  const int blocks = (int)std::min<size_t>((n + 255) / 256, 1024);
+  absmax_kernel<<<blocks, 256, 0, s>>>(x, n, reinterpret_cast<unsigned*>(out));
   return cudaGetLastError();
 }
 
@@ -227,6 +260,10 @@ cudaError_t launch_pack_latent(const void* x, int in_dtype, void* y, int out_dty
   if (!total) return cudaSuccess;
   dim3 g(nblk(total, 256)), blk(256);
 #define PL(TI, TO) pack_latent_kernel<TI, TO><<<g, blk, 0, s>>>((const TI*)x, (TO*)y, seg, src_row, B, Tmax, C, R)
+#define PLS(TI) pack_latent_split_kernel<TI><<<g, blk, 0, s>>>((const TI*)x, (__half*)y, seg, src_row, B, Tmax, C, R)
+  if (out_dtype == 3) {   // split [hi | lo] fp16
+    if (in_dtype == 0) PLS(float); else if (in_dtype == 1) PLS(__nv_bfloat16); else PLS(__half);
+  } else
   if (out_dtype == 0) {
     if (in_dtype == 0) PL(float, float); else if (in_dtype == 1) PL(__nv_bfloat16, float); else PL(__half, float);
   } else if (out_dtype == 1) {
@@ -235,6 +272,7 @@ cudaError_t launch_pack_latent(const void* x, int in_dtype, void* y, int out_dty
     if (in_dtype == 0) PL(float, __half); else if (in_dtype == 1) PL(__nv_bfloat16, __half); else PL(__half, __half);
   }
 #undef PL
+#undef PLS
   return cudaGetLastError();
 }
 

@@ -25,13 +25,15 @@ bool umma_k_packed_default(int Cin, int N);   // whether bvg_forward's image of 
 cudaError_t launch_repack_umma(const float* wp_tap_major, void* img, int dtype, int ntaps, int Cin, int N, float acc_img_scale,
                                bool small, cudaStream_t s, const float* out_scale = nullptr, const float* in_scale = nullptr,
                                const float* res_diag = nullptr, bool packed = false);
-// fp32 tensor-core mode helpers: weights [tap][Cin][N] -> [tap][3 Cin][N] = [W_hi; W_hi; W_lo] (bvg_conv_umma.cu);
+// fp32 tensor-core mode helpers: weights [tap][Cin][N] -> [tap][3 Cin][N] = S [2^-11 W_hi; W_lo; W_hi] (bvg_conv_umma.cu);
 // packed fp32 tensor [C/8][R][8] -> split bf16 tensor [2 C/8][R][8] = [hi chunks | lo chunks] (valid rows only)
-cudaError_t launch_split3_weights(const float* w_tap_major, float* w3, int ntaps, int Cin, int N, cudaStream_t s);
+cudaError_t launch_split3_weights(const float* w_tap_major, float* w3, int ntaps, int Cin, int N, float scale, cudaStream_t s);
+float split3_weight_scale(float absmax);   // the layer's power-of-two scale S for that image
+cudaError_t launch_absmax(const float* x, size_t n, float* out_zeroed, cudaStream_t s);
 cudaError_t launch_split_c8(const float* x, void* y_split, const SegDesc* seg, int B, int C, int R, int max_len, cudaStream_t s);
 cudaError_t launch_scale_vec(const float* x, const float* scale, float* y, int n, cudaStream_t s);   // y = x * scale
 cudaError_t launch_zero_guards(void* buf, int esize, const SegDesc* seg, int B, int C, int R, cudaStream_t s);
 // every packed buffer of a plan in one launch
 struct GuardJob { void* buf; const SegDesc* seg; int chunks, R, vec_per_row; };
-struct GuardJobs { GuardJob job[2 + 5 * 8]; int n; };
+struct GuardJobs { GuardJob job[3 + 5 * 8]; int n; };
 cudaError_t launch_zero_guards_all(const GuardJobs& jobs, int B, cudaStream_t s);

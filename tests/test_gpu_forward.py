@@ -129,14 +129,14 @@ def test_fp16_mode_saturates_instead_of_overflowing(gen):
 
 
 def test_auto_precision_follows_autocast(gen, golden_dir):
-    """precision="auto" (the constructor default): fp32 like the reference module unless the caller is inside
-    torch.amp.autocast, then the autocast dtype (infer.py:456, :613)."""
+    """precision="auto" (the constructor default): fp32 tensors like the reference module (the fp32 tensor-core mode)
+    unless the caller is inside torch.amp.autocast, then the autocast dtype (infer.py:456, :613)."""
     from b200vgan import synth
     g = np.load(os.path.join(golden_dir, "forward_cfg1.npz"))
     x = torch.as_tensor(synth.make_latents(1, 0, 1, 118)).cuda()
     emb = torch.as_tensor(g["emb"]).cuda()
     gen.precision = "auto"
-    assert gen.resolved_precision() == "fp32"
+    assert gen.resolved_precision() == "fp32tc"
     w32 = gen.forward_with_embedding(x, emb).cpu().numpy()
     with torch.amp.autocast("cuda", dtype=torch.float16):
         assert gen.resolved_precision() == "fp16"
@@ -544,3 +544,87 @@ def test_latent_handoff_device_resident_and_graph_replay(gen):
         assert not torch.equal(eager[i], eager2[i])
         off += n
     gen.precision = "fp32"
+
+
+# ---- fp32 tensor-core mode (BVG_MODE_FP32_TC, precision="fp32tc"): fp32 storage, convolutions as three bf16 tensor-core
+# passes over split operands.  Same gates as the fp32 parity mode: max-abs <= 1e-3, mel-L1 <= 1e-3.
+
+def test_fp32tc_tiny_and_cfg1_match_reference(gen, golden_dir):
+    from b200vgan import synth
+    g = np.load(os.path.join(golden_dir, "forward_tiny.npz"))
+    wav = _run(gen, g["x"], g["emb"], "fp32tc")
+    assert wav.shape == g["wav"].shape
+    for b in range(wav.shape[0]):
+        _gate_fp32(f"fp32tc tiny item {b}", wav[b, 0], g["wav"][b, 0])
+    g1 = np.load(os.path.join(golden_dir, "forward_cfg1.npz"))
+    x = synth.make_latents(1, 0, 1, 118)
+    wav = _run(gen, x, g1["emb"], "fp32tc")
+    _gate_fp32("fp32tc cfg1 (reference waveform)", wav[0, 0], g1["wav"][0, 0])
+
+
+def test_fp32tc_dropin_call_under_no_autocast(gen, golden_dir):
+    """wav, _ = bigvgan(latent, mel_ref) in the fp32 tensor-core mode, speaker encoder included."""
+    g = np.load(os.path.join(golden_dir, "forward_tiny.npz"))
+    gen.precision = "fp32tc"
+    try:
+        wav, aux = gen(torch.as_tensor(g["x"]).cuda(), torch.as_tensor(g["mel"]).cuda())
+    finally:
+        gen.precision = "fp32"
+    assert aux is None and wav.dtype == torch.float32
+    assert np.abs(wav.cpu().numpy() - g["wav"]).max() <= FP32_MAXABS
+
+
+def test_fp32tc_cfg2_tracks_fp32_mode_and_oracle(gen):
+    """Config 2 (B=16 x 10 s): every item against the FFMA parity mode, item 7 against the CPU oracle."""
+    from b200vgan import synth
+    x = synth.make_latents(2, 0, 16, 235)
+    emb = synth.make_speaker_embedding(B=1)
+    w32 = _run(gen, x, emb, "fp32")
+    wtc = _run(gen, x, emb, "fp32tc")
+    d = float(np.abs(wtc - w32).max())
+    print("cfg2 fp32tc-vs-fp32-mode max-abs", d, "SNR dB", O.snr_db(w32.ravel(), wtc.ravel()))
+    assert d <= 5e-4
+    ref = _oracle(x[7:8], emb)[0, 0]
+    _gate_fp32("fp32tc cfg2 item 7", wtc[7, 0], ref)
+
+
+def test_fp32tc_ragged_and_long_form(gen):
+    """Ragged batch (each segment = its stand-alone decode, as in the other modes) and the 60 s long form against the
+    FFMA parity mode (which test_cfg4_long_form_vs_oracle gates against the oracle)."""
+    from b200vgan import synth
+    emb = synth.make_speaker_embedding(B=1)
+    lens = [37, 5, 118, 64]
+    x = synth.make_latents(3, 0, 4, max(lens))
+    both = _run(gen, x, emb, "fp32tc", lens=lens)
+    for b, n in enumerate(lens):
+        one = _run(gen, x[b:b + 1, :n], emb, "fp32tc")
+        assert np.array_equal(both[b, 0, :n * 1024], one[0, 0]), b
+        assert not both[b, 0, n * 1024:].any()
+    T = 1407
+    x = synth.make_latents(4, 0, 1, T)
+    w32 = _run(gen, x, emb, "fp32")[0, 0]
+    wtc = _run(gen, x, emb, "fp32tc")[0, 0]
+    d = float(np.abs(wtc - w32).max())
+    print("cfg4 fp32tc-vs-fp32-mode max-abs", d)
+    assert d <= 5e-4
+    edge = 36000
+    assert np.abs(wtc[:edge] - w32[:edge]).max() <= 5e-4 and np.abs(wtc[-edge:] - w32[-edge:]).max() <= 5e-4
+
+
+def test_fp32tc_pcm16_and_ragged_rows(gen):
+    """The fused int16 output and the back-to-back ragged entry point in the fp32 tensor-core mode."""
+    from b200vgan import synth
+    emb = torch.as_tensor(synth.make_speaker_embedding(B=1)).cuda()
+    frames = [9, 33, 17]
+    rows = torch.as_tensor(np.random.default_rng(5).standard_normal((sum(frames), 1024), dtype=np.float32)).cuda()
+    gen.precision = "fp32tc"
+    try:
+        flat = gen.forward_ragged(rows, frames, emb).cpu().numpy()
+        pcm = gen.forward_ragged(rows, frames, emb, pcm16=True).cpu().numpy()
+    finally:
+        gen.precision = "fp32"
+    ref = gen.forward_ragged(rows, frames, emb).cpu().numpy()
+    assert flat.shape == ref.shape == (sum(frames) * 1024,)
+    assert np.abs(flat - ref).max() <= 5e-4
+    want = np.clip(32767.0 * flat, -32767.0, 32767.0).astype(np.int16)
+    assert np.abs(pcm.astype(np.int32) - want.astype(np.int32)).max() <= 1

@@ -166,12 +166,16 @@ def test_gather_world_size_2_gloo():
 
 
 def test_precision_resolution_follows_autocast(module_cpu):
-    """precision="auto" (constructor default): fp32 like the reference module, the autocast dtype inside an autocast
-    region (infer.py:456, :613); explicit modes are taken as given; anything else is rejected."""
+    """precision="auto" (constructor default): fp32 tensors like the reference module (the fp32 tensor-core mode, or the
+    CUDA-core parity mode when AUTO_FP32_PRECISION says so), the autocast dtype inside an autocast region (infer.py:456,
+    :613); explicit modes are taken as given; anything else is rejected."""
     from b200vgan import lib
     m = module_cpu
-    assert m.precision == "auto" and m.resolved_precision() == "fp32" and m._mode() == lib.MODE_FP32
-    for p, mode in (("fp32", lib.MODE_FP32), ("bf16", lib.MODE_BF16), ("fp16", lib.MODE_F16)):
+    assert m.precision == "auto" and m.resolved_precision() == "fp32tc" and m._mode() == lib.MODE_FP32_TC
+    m.AUTO_FP32_PRECISION = "fp32"          # (instance override of the class default)
+    assert m.resolved_precision() == "fp32" and m._mode() == lib.MODE_FP32
+    del m.AUTO_FP32_PRECISION
+    for p, mode in (("fp32", lib.MODE_FP32), ("fp32tc", lib.MODE_FP32_TC), ("bf16", lib.MODE_BF16), ("fp16", lib.MODE_F16)):
         m.precision = p
         assert m.resolved_precision() == p and m._mode() == mode
     m.precision = "int8"
