@@ -141,7 +141,7 @@ cudaError_t launch_act_c8(const ActArgs& a, int dtype, bool precise, cudaStream_
   static const int use_mma = [] { const char* e = getenv("BVG_ACT_MMA"); return e ? atoi(e) : 1; }();
   if (dtype == 2) return precise ? cudaErrorInvalidValue : launch_act_c8_mma(a, dtype, s);   // fp16 storage: tensor-core kernel only
   if (use_mma && dtype == 1 && !precise) return launch_act_c8_mma(a, dtype, s);
-  if (a.prescaled) return cudaErrorInvalidValue;   // only the tensor-core kernel has the pre-scaled variant
+  if (a.prescaled || a.extra_jobs) return cudaErrorInvalidValue;   // only the tensor-core kernel has the pre-scaled variant / grouped launches
   return launch_act_c8_v2(a, dtype, precise, rt, s);
 }
 

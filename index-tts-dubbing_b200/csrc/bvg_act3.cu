@@ -126,16 +126,29 @@ __device__ __forceinline__ float tap(int k) {   // f[k], 0 outside 0..11 (kaiser
   return f[k < 6 ? k : 11 - k];
 }
 
+struct ActExtraJobs {
+  const void* x[2];
+  void* y[2];
+  const float* alpha[2];
+  const float* inv_beta[2];
+};
+
 // UP_LO: add the rounding residual of the up-FIR taps as a second MMA per column tile.
 // PRE: the input is pre-scaled by 2 alpha per channel (u' = 2 alpha u comes straight out of the up-FIR), the output stays
 // scaled:  v = u' - (2 alpha h) cos(u') = 2 alpha (s - h),  y' = down(v) + 2 alpha h = 2 alpha y  -- one multiply per sample less.
 template <typename T, bool UP_LO, bool PRE = false>
 __global__ void __launch_bounds__(WPB * 32, MINB)
-act1d_c8_mma_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __restrict__ alpha,
-                    const float* __restrict__ inv_beta, const SegDesc* __restrict__ seg, int R, int ntiles, int nchunks,
+act1d_c8_mma_kernel(const T* __restrict__ x0, T* __restrict__ y0, const float* __restrict__ alpha0,
+                    const float* __restrict__ inv_beta0, const SegDesc* __restrict__ seg, int R, int ntiles, int nchunks,
                     int tw /* output rows per tile (multiple of 8, <= TWMAX) */,
-                    int GT /* consecutive time tiles a warp processes per stream: amortises the constant set-up */) {
+                    int GT /* consecutive time tiles a warp processes per stream: amortises the constant set-up */,
+                    const ActExtraJobs extra /* blockIdx.y = 1, 2: the same geometry on other tensors / parameters */) {
   extern __shared__ uint4 smem4[];
+  const int job = blockIdx.y;
+  const T* __restrict__ x = job == 0 ? x0 : reinterpret_cast<const T*>(job == 1 ? extra.x[0] : extra.x[1]);
+  T* __restrict__ y = job == 0 ? y0 : reinterpret_cast<T*>(job == 1 ? extra.y[0] : extra.y[1]);
+  const float* __restrict__ alpha = job == 0 ? alpha0 : (job == 1 ? extra.alpha[0] : extra.alpha[1]);
+  const float* __restrict__ inv_beta = job == 0 ? inv_beta0 : (job == 1 ? extra.inv_beta[0] : extra.inv_beta[1]);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int b = blockIdx.z;
   const SegDesc sd = seg[b];
@@ -424,7 +437,12 @@ cudaError_t launch_t(const ActArgs& a, cudaStream_t s) {
   }
   const int nchunks = a.C / 8;
   static const int force_tw = [] { const char* e = getenv("BVG_ACT_TW"); return e ? atoi(e) : 0; }();
-  ActTiling tl = choose_tiling(a.max_len, nchunks, a.B, sms_of_dev[dev]);
+  const int njobs = 1 + (a.extra_jobs > 0 ? (a.extra_jobs > 2 ? 2 : a.extra_jobs) : 0);
+  ActExtraJobs extra{};
+  for (int j = 0; j + 1 < njobs; ++j) {
+    extra.x[j] = a.xj[j]; extra.y[j] = a.yj[j]; extra.alpha[j] = a.alphaj[j]; extra.inv_beta[j] = a.inv_betaj[j];
+  }
+  ActTiling tl = choose_tiling(a.max_len, nchunks, a.B * njobs, sms_of_dev[dev]);
   static const int force_gt = [] { const char* e = getenv("BVG_ACT_GT"); return e ? atoi(e) : 0; }();
   if (force_tw >= 8 && force_tw <= TWMAX) {
     tl.tw = force_tw / 8 * 8; tl.ntiles = (a.max_len + tl.tw - 1) / tl.tw; tl.GT = tl.ntiles >= 2 ? 2 : 1;
@@ -433,18 +451,18 @@ cudaError_t launch_t(const ActArgs& a, cudaStream_t s) {
   static const int dbg = [] { const char* e = getenv("BVG_ACT_DEBUG"); return e ? atoi(e) : 0; }();
   if (dbg) fprintf(stderr, "act: C %d max_len %d B %d -> tw %d ntiles %d GT %d (resident warps %lld)\n", a.C, a.max_len, a.B, tl.tw, tl.ntiles, tl.GT, sms_of_dev[dev]);
   const int nitems = ((tl.ntiles + tl.GT - 1) / tl.GT) * nchunks;
-  dim3 grid((nitems + 2 * WPB - 1) / (2 * WPB), 1, a.B), block(WPB * 32);
+  dim3 grid((nitems + 2 * WPB - 1) / (2 * WPB), njobs, a.B), block(WPB * 32);
   // BVG_ACT_MMA_UPLO=1 adds the rounding residual of the up-FIR taps (a second MMA per column tile): +0.4 dB of SNR
   // on config 1 in the bf16 mode for ~4 % of the step time; off by default.
   static const int up_lo = [] { const char* e = getenv("BVG_ACT_MMA_UPLO"); return e ? atoi(e) : 0; }();
   if (a.prescaled)   // (the hi + lo tap split is a bf16-accuracy aid of the plain variant only)
     return launch_pdl(act1d_c8_mma_kernel<T, false, true>, grid, block, smem, s, (const T*)a.x, (T*)a.y, a.alpha, a.inv_beta, a.seg, a.R,
-                      tl.ntiles, nchunks, tl.tw, tl.GT);
+                      tl.ntiles, nchunks, tl.tw, tl.GT, extra);
   if (!up_lo)
     return launch_pdl(act1d_c8_mma_kernel<T, false>, grid, block, smem, s, (const T*)a.x, (T*)a.y, a.alpha, a.inv_beta, a.seg, a.R,
-                      tl.ntiles, nchunks, tl.tw, tl.GT);
+                      tl.ntiles, nchunks, tl.tw, tl.GT, extra);
   return launch_pdl(act1d_c8_mma_kernel<T, true>, grid, block, smem, s, (const T*)a.x, (T*)a.y, a.alpha, a.inv_beta, a.seg, a.R,
-                    tl.ntiles, nchunks, tl.tw, tl.GT);
+                    tl.ntiles, nchunks, tl.tw, tl.GT, extra);
 }
 
 }  // namespace

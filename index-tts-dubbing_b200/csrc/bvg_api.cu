@@ -61,7 +61,7 @@ struct ConvLayer {
   const float* fold_res = nullptr;   // [Cout] factor on the residual input (the residual stream is stored pre-scaled)
   float* fold_buf = nullptr;         // device storage owned by this layer for fold_out / fold_res products ([2 * Cout])
   bool k_packed = false;             // the UMMA images are K-packed (24-channel layers, bvg_conv_umma.cu)
-  void* w_umma3 = nullptr;           // fp32 tensor-core mode: fp16 image of S [W_hi; 2^-11 W_hi; W_lo] (3 Cin input channels), built on first use
+  void* w_umma3 = nullptr;           // fp32 tensor-core mode: fp16 image of S [2^-11 W_hi; W_lo; W_hi] (3 Cin input channels), built on first use
   float tc32_acc_scale = 1.f;        // 1 / S
   void setup() {
     if (!transposed) {
@@ -180,6 +180,10 @@ struct bvg_plan {
   size_t ws_bytes = 0;
   size_t off_lat = 0, off_pre = 0, off_bias = 0, off_split0 = 0;
   std::vector<size_t> off_U, off_X, off_A, off_Y, off_XS;
+  // lockstep mode (16-bit modes): the nk AMP blocks of a stage advance together and share their Activation1d launches, so
+  // blocks 1 .. nk-1 get their own X / A / Y buffers ([g][j-1]; block 0 uses off_X / off_A / off_Y)
+  bool lockstep = false;
+  std::vector<std::vector<size_t>> off_Xj, off_Aj, off_Yj;
   int bias_stride = 0;
   std::vector<int> bias_off;    // per cond layer (0 = pre, 1.. = ups)
   uint64_t uid = 0;
@@ -339,7 +343,30 @@ int run_act(const ActLayer& A, const bvg_plan* p, int g, const void* x, void* y,
   return 0;
 }
 
-// BVG_MODE_FP32_TC: the S [W_hi; 2^-11 W_hi; W_lo] images of every convolution on the path, built once per handle on the
+// The same-geometry activations of the nk AMP blocks in one launch (tensor-core kernel); layers whose pre-scaled flags differ
+// fall back to one launch each.
+int run_act_group(const ActLayer* const* A, int n, const bvg_plan* p, int g, const void* const* x, void* const* y, cudaStream_t s) {
+  bool same = n >= 2 && n <= 3;
+  for (int j = 1; j < n; ++j) same = same && A[j]->prescaled == A[0]->prescaled;
+  if (!same) {
+    for (int j = 0; j < n; ++j)
+      if (run_act(*A[j], p, g, x[j], y[j], s)) return 1;
+    return 0;
+  }
+  ActArgs aa{x[0], y[0], A[0]->alpha, A[0]->inv_beta, p->seg_dev + (size_t)g * p->B, p->R[g], p->C[g], p->B, p->maxlen[g]};
+  aa.prescaled = A[0]->prescaled ? 1 : 0;
+  aa.extra_jobs = n - 1;
+  for (int j = 1; j < n; ++j) {
+    aa.xj[j - 1] = x[j]; aa.yj[j - 1] = y[j]; aa.alphaj[j - 1] = A[j]->alpha; aa.inv_betaj[j - 1] = A[j]->inv_beta;
+  }
+  const double bytes = 2.0 * n * p->C[g] * (double)p->sumlen[g] * p->esize;
+  ProfScope ps(p->h, s, PROF_ACT, 0.0, bytes);
+  CK(launch_act_c8(aa, p->dtype, false, s));
+  ++p->h->launch_counter;
+  return 0;
+}
+
+// BVG_MODE_FP32_TC: the S [2^-11 W_hi; W_lo; W_hi] images of every convolution on the path, built once per handle on the
 // stream of the first forward that needs them (the 16-bit modes never pay for them: + 3x the fp16 weights = 0.68 GB).
 int build_tc32_image(bvg_handle* h, ConvLayer& L, float* w3, float absmax, cudaStream_t s) {
   const size_t bytes = umma_weight_image_bytes(L.ntaps, 3 * L.Cin, L.N);
@@ -823,6 +850,24 @@ int bvg_plan_create(bvg_handle* h, int32_t B, const int32_t* frames, int32_t mod
     p->off_U[g] = take(bytes); p->off_X[g] = take(bytes); p->off_A[g] = take(bytes);
     p->off_Y[g] = take(bytes); p->off_XS[g] = take(bytes);
   }
+  {
+    static const int group = [] {
+      const char* e = getenv("BVG_ACT_GROUP");
+      const char* f = getenv("BVG_FUSE_ACT");   // the fused kernel and the register-streamed kernel keep one block at a time
+      const char* m = getenv("BVG_ACT_MMA");
+      if ((f && atoi(f)) || (m && !atoi(m))) return 0;
+      return e ? atoi(e) : 1;
+    }();
+    p->lockstep = group && (mode == BVG_MODE_BF16 || mode == BVG_MODE_F16) && h->nk >= 2 && h->nk <= 3;
+    p->off_Xj.resize(ng); p->off_Aj.resize(ng); p->off_Yj.resize(ng);
+    if (p->lockstep)
+      for (int g = 1; g < ng; ++g) {
+        const size_t bytes = (size_t)p->C[g] * p->R[g] * es;
+        for (int j = 1; j < h->nk; ++j) {
+          p->off_Xj[g].push_back(take(bytes)); p->off_Aj[g].push_back(take(bytes)); p->off_Yj[g].push_back(take(bytes));
+        }
+      }
+  }
   p->bias_off.resize(ng);
   int bo = 0;
   for (int g = 0; g < ng; ++g) { p->bias_off[g] = bo; bo += p->C[g]; }
@@ -905,6 +950,9 @@ static int forward_impl(bvg_handle* h, bvg_plan* p, const void* latent, int32_t 
     for (int g = 1; g < ng; ++g) {
       for (size_t o : {p->off_U[g], p->off_X[g], p->off_Y[g], p->off_XS[g]}) add(o, g, p->C[g]);
       add(p->off_A[g], g, p->C[g], tc32);
+      for (size_t o : p->off_Xj[g]) add(o, g, p->C[g]);
+      for (size_t o : p->off_Aj[g]) add(o, g, p->C[g]);
+      for (size_t o : p->off_Yj[g]) add(o, g, p->C[g]);
     }
     ProfScope ps(h, s, PROF_OTHER, 0.0, 0.0);
     CK(launch_zero_guards_all(jobs, B, s));
@@ -944,6 +992,38 @@ static int forward_impl(bvg_handle* h, bvg_plan* p, const void* latent, int32_t 
     }
     if (run_conv(h->ups[i], p, g - 1, g, stage_in, U, nullptr, biasb + p->bias_off[g], p->bias_stride, 1.f, 0, s))
       return 1;
+    if (p->lockstep) {
+      // The nk AMP blocks (models.py:237-243) are independent until their outputs are averaged: step them together, one
+      // Activation1d launch per step for all of them (the kernel's fixed cost -- a warp's latency through two tiles plus
+      // the tail of the last wave, ~16 us -- is paid once instead of nk times), their convolutions back to back.
+      const int nk = h->nk, nd = h->nd;
+      char *Xj[3] = {X, nullptr, nullptr}, *Aj[3] = {A, nullptr, nullptr}, *Yj[3] = {Y, nullptr, nullptr};
+      for (int j = 1; j < nk; ++j) {
+        Xj[j] = ws + p->off_Xj[g][j - 1]; Aj[j] = ws + p->off_Aj[g][j - 1]; Yj[j] = ws + p->off_Yj[g][j - 1];
+      }
+      for (int m = 0; m < nd; ++m) {
+        const bool last = m == nd - 1;
+        const ActLayer* a1[3]; const ActLayer* a2[3]; const void* in[3]; void* outA[3]; const void* inY[3];
+        for (int j = 0; j < nk; ++j) {
+          const int rb = i * nk + j;
+          a1[j] = &h->acts[(size_t)rb * 2 * nd + 2 * m];
+          a2[j] = &h->acts[(size_t)rb * 2 * nd + 2 * m + 1];
+          in[j] = m == 0 ? U : Xj[j];
+          outA[j] = Aj[j];
+          inY[j] = Yj[j];
+        }
+        if (run_act_group(a1, nk, p, g, in, outA, s)) return 1;
+        for (int j = 0; j < nk; ++j) {
+          const ConvLayer& c1 = h->c1[(size_t)(i * nk + j) * nd + m];
+          if (run_conv(c1, p, g, g, Aj[j], Yj[j], nullptr, c1.bias, 0, 1.f, 0, s)) return 1;
+        }
+        if (run_act_group(a2, nk, p, g, inY, outA, s)) return 1;
+        for (int j = 0; j < nk; ++j) {
+          const ConvLayer& c2 = h->c2[(size_t)(i * nk + j) * nd + m];
+          if (run_conv(c2, p, g, g, Aj[j], last ? XS : Xj[j], in[j], c2.bias, 0, last ? 1.f / nk : 1.f, last && j > 0, s)) return 1;
+        }
+      }
+    } else
     for (int j = 0; j < h->nk; ++j) {          // AMP blocks (models.py:237-243)
       const int rb = i * h->nk + j;
       for (int m = 0; m < h->nd; ++m) {        // AMPBlock1.forward (models.py:65-74)
@@ -1114,7 +1194,7 @@ int conv_op(bool transposed, const float* x, const float* w, const float* bias, 
     }
   }
   if (tc32) {
-    // [hi | lo] fp16 split of the fp32 input, S [W_hi; 2^-11 W_hi; W_lo] weight image, fp32 epilogue
+    // [hi | lo] fp16 split of the fp32 input, S [2^-11 W_hi; W_lo; W_hi] weight image, fp32 epilogue
     void* xs; float *w3, *amax, amax_h = 0.f;
     if (tmp.alloc(&xs, (size_t)Cin * Rin * 4) || tmp.alloc((void**)&w3, 3 * (size_t)Cin * Cout * k * sizeof(float)) ||
         tmp.alloc((void**)&amax, sizeof(float))) return 1;

@@ -78,6 +78,13 @@ struct ActArgs {
   // 16-bit tensor-core kernel only: x holds 2*alpha*x_true per channel (folded into the producing convolution's weights)
   // and y receives 2*alpha*y_true (unfolded by the consuming convolution's weights): saves the per-sample argument multiply
   int prescaled;
+  // tensor-core kernel only: up to two more activations of the same geometry (other tensors, other parameters) in the same
+  // launch -- the three AMP blocks of a stage run in lockstep (bvg_api.cu) and share their Activation1d launches
+  int extra_jobs;
+  const void* xj[2];
+  void* yj[2];
+  const float* alphaj[2];
+  const float* inv_betaj[2];
   int fast_fp32;   // fp32 kernel only: fp32 tensor-core mode's activation arithmetic (see launch_act_c8_v2)
   int split_out;   // fp32 kernel only: y is a split bf16 tensor [hi chunks | lo chunks] (fp32 tensor-core mode)
 };

@@ -35,5 +35,5 @@ cudaError_t launch_scale_vec(const float* x, const float* scale, float* y, int n
 cudaError_t launch_zero_guards(void* buf, int esize, const SegDesc* seg, int B, int C, int R, cudaStream_t s);
 // every packed buffer of a plan in one launch
 struct GuardJob { void* buf; const SegDesc* seg; int chunks, R, vec_per_row; };
-struct GuardJobs { GuardJob job[3 + 5 * 8]; int n; };
+struct GuardJobs { GuardJob job[3 + 11 * 8]; int n; };
 cudaError_t launch_zero_guards_all(const GuardJobs& jobs, int B, cudaStream_t s);

@@ -628,3 +628,40 @@ def test_fp32tc_pcm16_and_ragged_rows(gen):
     assert np.abs(flat - ref).max() <= 5e-4
     want = np.clip(32767.0 * flat, -32767.0, 32767.0).astype(np.int16)
     assert np.abs(pcm.astype(np.int32) - want.astype(np.int32)).max() <= 1
+
+
+def test_lockstep_blocks_equal_sequential_blocks(tmp_path):
+    """BVG_ACT_GROUP (default 1): the three AMP blocks of a stage advance in lockstep and share their Activation1d launches.
+    Same kernels on the same tensors in another order: the waveform must not change by a bit (bf16 and fp16 modes, ragged
+    batch).  The switch is read once per process, so each setting runs in its own interpreter."""
+    import subprocess
+    import sys
+    code = r'''
+import os, sys
+sys.path.insert(0, os.path.join(os.getcwd(), "index-tts-dubbing_b200"))
+import numpy as np, torch
+from b200vgan import synth
+from b200vgan.model import BigVGAN
+g = BigVGAN(dict(synth.H_DEFAULT), precision="bf16")
+sd = synth.make_state_dict(1234, with_speaker_encoder=False)
+g.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()}, strict=False)
+g = g.to("cuda"); g.remove_weight_norm(); g.eval()
+x = torch.from_numpy(synth.make_latents(9, 0, 3, 40)).cuda()
+emb = torch.from_numpy(synth.make_speaker_embedding(B=1)).cuda()
+out = {}
+for prec in ("bf16", "fp16"):
+    g.precision = prec
+    out[prec] = g.forward_with_embedding(x, emb, x_lens=[40, 7, 23]).cpu().numpy()
+    out[prec + "_launches"] = np.int64(g.num_launches([40, 7, 23]))
+np.savez(sys.argv[1], **out)
+'''
+    res = {}
+    for v in ("0", "1"):
+        path = str(tmp_path / f"group{v}.npz")
+        env = dict(os.environ, BVG_ACT_GROUP=v)
+        subprocess.run([sys.executable, "-c", code, path], check=True, env=env, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                       timeout=600)
+        res[v] = np.load(path)
+    for prec in ("bf16", "fp16"):
+        assert np.array_equal(res["0"][prec], res["1"][prec]), prec
+        assert int(res["1"][prec + "_launches"]) == int(res["0"][prec + "_launches"]) - 72   # 6 stages x 6 steps x 2 launches saved
