@@ -269,7 +269,7 @@ ConvArgs make_conv_args(const ConvLayer& L, const bvg_plan* p, int gin, int gout
 }
 
 int run_conv(const ConvLayer& L, const bvg_plan* p, int gin, int gout, const void* x, void* y, const void* res,
-             const float* bias, int bias_bstride, float scale, int accumulate, cudaStream_t s) {
+             const float* bias, int bias_bstride, float scale, int accumulate, cudaStream_t s, int pdl_mode = 0) {
   // algorithmic work of this launch: 2 * Cin * taps * N MACs per input row (valid rows only)
   const double flops = 2.0 * L.Cin * L.ntaps * L.N * (double)p->sumlen[gin];
   const double bytes = ((double)L.Cin * p->sumlen[gin] + (double)L.Cout * p->sumlen[gout] * (res ? 2 : 1)) * p->esize;
@@ -293,6 +293,7 @@ int run_conv(const ConvLayer& L, const bvg_plan* p, int gin, int gout, const voi
   if (p->mode != BVG_MODE_FP32 && L.w_umma) {   // (BVG_MODE_FP32_TC returned above)
     const float* ubias = (L.bias_umma && bias == L.bias) ? L.bias_umma : bias;   // the image's output channels are pre-scaled
     ConvArgs a = make_conv_args(L, p, gin, gout, x, y, res, ubias, bias_bstride, scale, accumulate, true);
+    a.pdl_mode = pdl_mode;
     if (conv_umma_supported(a)) {
       ProfScope ps(p->h, s, PROF_CONV_TC, flops, bytes);
       CK(launch_conv_umma(a, s));
@@ -1013,14 +1014,18 @@ static int forward_impl(bvg_handle* h, bvg_plan* p, const void* latent, int32_t 
           inY[j] = Yj[j];
         }
         if (run_act_group(a1, nk, p, g, in, outA, s)) return 1;
+        // the nk convolutions of a step do not depend on each other: the later ones start under their predecessor's tail
+        // (ConvArgs::pdl_mode); the last step's second convolutions accumulate into XS one after the other
+        static const int indep = [] { const char* e = getenv("BVG_PDL_INDEP"); return e ? atoi(e) : 1; }();
         for (int j = 0; j < nk; ++j) {
           const ConvLayer& c1 = h->c1[(size_t)(i * nk + j) * nd + m];
-          if (run_conv(c1, p, g, g, Aj[j], Yj[j], nullptr, c1.bias, 0, 1.f, 0, s)) return 1;
+          if (run_conv(c1, p, g, g, Aj[j], Yj[j], nullptr, c1.bias, 0, 1.f, 0, s, indep ? (j == 0 ? 1 : 2) : 0)) return 1;
         }
         if (run_act_group(a2, nk, p, g, inY, outA, s)) return 1;
         for (int j = 0; j < nk; ++j) {
           const ConvLayer& c2 = h->c2[(size_t)(i * nk + j) * nd + m];
-          if (run_conv(c2, p, g, g, Aj[j], last ? XS : Xj[j], in[j], c2.bias, 0, last ? 1.f / nk : 1.f, last && j > 0, s)) return 1;
+          if (run_conv(c2, p, g, g, Aj[j], last ? XS : Xj[j], in[j], c2.bias, 0, last ? 1.f / nk : 1.f, last && j > 0, s,
+                       (indep && !last) ? (j == 0 ? 1 : 2) : 0)) return 1;
         }
       }
     } else

@@ -59,6 +59,13 @@ struct ConvArgs {
   // values followed by as many chunks of fp16 remainders 2^11 (x - hi) (22 significand bits together, split_f32 below) --
   // and Cin counts 3 x the real input channels: the GEMM multiplies [lo | hi | hi] with the fp16 weight image
   // S [2^-11 W_hi; W_lo; W_hi] (S = the layer's power-of-two scale, acc_scale = 1 / S); y / res are fp32 packed tensors
+  // programmatic dependent launch between INDEPENDENT convolutions (the same step of the nk AMP blocks, bvg_api.cu):
+  //   0  trigger, then wait for the previous kernel before touching memory (the default chain);
+  //   1  wait, THEN trigger: a successor of kind 2 may assume everything before this kernel has completed;
+  //   2  independent of its predecessor (which is of kind 1 or 2): no wait before the work, so its first tiles run under
+  //      the predecessor's tail; it waits just before it exits, which keeps completion order transitive for whoever
+  //      waits on it.
+  int pdl_mode;
   float acc_scale;   // f32io: factor on the accumulator (undoes the power-of-two scale of the fp16 weight image)
   int f32io;
   int split3_chunks;

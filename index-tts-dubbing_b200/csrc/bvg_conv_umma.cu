@@ -392,8 +392,13 @@ __global__ void __launch_bounds__(FUSE ? NTHREADS_FUSED : 64 + 32 * EPW, 1) conv
   const uint32_t tmem_base = *tmem_slot;
   // programmatic dependent launch: the set-up above (barriers, TMEM, bias staging -- launch constants only) may run
   // while the previous kernel drains; activations are read and outputs written only after it has completed
-  pdl_trigger();
-  pdl_wait();
+  if (a.pdl_mode == 1) {
+    pdl_wait();
+    pdl_trigger();
+  } else {
+    pdl_trigger();
+    if (a.pdl_mode != 2) pdl_wait();
+  }
 
   // low-overhead event trace (CTA 0 only): per-role ring in shared memory, flushed at kernel end
   unsigned long long* tr_smem = reinterpret_cast<unsigned long long*>(smem + (SMEM_MAX - 4 * 1024 * 8));
@@ -1044,6 +1049,7 @@ __global__ void __launch_bounds__(FUSE ? NTHREADS_FUSED : 64 + 32 * EPW, 1) conv
     tc_fence_after();
     tmem_dealloc(tmem_base, (uint32_t)ka.tmem_cols);
   }
+  if (a.pdl_mode == 2) pdl_wait();   // (see ConvArgs::pdl_mode)
 }
 
 // fp32 [tap][Cin][N]  ->  bf16 images [ntile][kb][tap][chunk KC][n BN][8]
