@@ -11,11 +11,14 @@ ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpuru
     python tools/profile_step.py --iters 2 > gpurun_out/ncu_launch_$TAG.log 2>&1
 echo "launch list rc=$?"
 python tools/profile_step.py --iters 1 > gpurun_out/plain2_$TAG.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:conv_umma -s 14 -c 1 -o gpurun_out/prof_conv_s0k11_$TAG \
+ncu --set full --clock-control none --import-source on -k regex:conv_umma -s 4 -c 1 -o gpurun_out/prof_conv_s0k11_$TAG \
     python tools/profile_step.py --iters 1 > gpurun_out/ncu_full_conv_$TAG.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:act1d_c8 -s 90 -c 1 -o gpurun_out/prof_act_s5_$TAG \
+ncu --set full --clock-control none --import-source on -k regex:act1d_c8 -s 30 -c 1 -o gpurun_out/prof_act_s5_$TAG \
     python tools/profile_step.py --iters 1 > gpurun_out/ncu_full_act_$TAG.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:conv_umma -s 109 -c 1 -o gpurun_out/prof_conv_s5k11_$TAG \
+ncu --set full --clock-control none --import-source on -k regex:conv_umma -s 99 -c 1 -o gpurun_out/prof_conv_s5k11_$TAG \
     python tools/profile_step.py --iters 1 > gpurun_out/ncu_full_conv5_$TAG.log 2>&1
 echo "ncu full rc=$?"
+# (lockstep launch order: conv launch 4 = stage 0, k = 11, m = 0 first convolution; 99 = the same of stage 5; activation launch 30 =
+#  the first grouped launch of stage 5, three blocks in one grid)
+timeout 300 python bench.py --precision fp32tc --steps 5 --warmup 3 --no-cpu-baseline --no-srt > gpurun_out/bench_fp32tc_$TAG.json 2> gpurun_out/bench_fp32tc_$TAG.err; echo "bench fp32tc rc=$?"
 head -c 1500 gpurun_out/bench_$TAG.json
