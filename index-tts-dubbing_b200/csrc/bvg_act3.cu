@@ -398,7 +398,8 @@ act1d_c8_mma_kernel(const T* __restrict__ x0, T* __restrict__ y0, const float* _
 // Tile length / tiles per warp for a launch (measured: tools/gpu_act_tiling.sh, profiles/r2_act_tiling_sweep.txt).
 //   * more than one wave of warps: balanced tiles of at most TWMAX rows (long tiles amortise the 32 halo rows and the
 //     per-tile set-up; between 1 and 8 waves the tile length hardly matters, wave-quantisation models did not predict
-//     the measurements), two consecutive tiles per warp from 8 waves on;
+//     the measurements), two consecutive tiles per warp from 4 waves on (with the three AMP blocks of a stage in one launch
+//     stage 1 of config 2 -- 5.2 waves -- runs 0.60 -> 0.51 ms per step with two tiles per warp; profiles/r2g_act_tiling.txt);
 //   * at most one wave (short segments, small batches): the kernel is bound by one warp's latency, so as many tiles
 //     as still fit one wave (tiles of at least 32 rows).
 struct ActTiling { int tw, ntiles, GT; };
@@ -413,7 +414,7 @@ ActTiling choose_tiling(int max_len, int nchunks, int B, long long slots /* resi
   }
   const int tw = tw_of(nt);
   const int nt_eff = (max_len + tw - 1) / tw;
-  return ActTiling{tw, nt_eff, warps_of(nt_eff) >= 8 * slots ? 2 : 1};
+  return ActTiling{tw, nt_eff, warps_of(nt_eff) >= 4 * slots ? 2 : 1};
 }
 
 template <typename T>
