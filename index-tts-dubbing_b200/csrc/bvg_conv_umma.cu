@@ -33,6 +33,14 @@
 // between the producer (raw rows) and the MMA issuer (activated A operand); measured slower than the
 // separate activation pass in round 1, kept for the next round.
 //
+// Round 2 additions: fp16 storage (template F16: kind::f16 on fp16 operands, saturating stores); K-packed images for the
+// 24-channel layers and 64-column n-tiles for small batches (make_tiling); and the fp32 tensor-core mode (template F32IO):
+// the input is a split fp16 tensor [hi | 2^11 lo] walked as 3 Cin channels against S [2^-11 W_hi; W_lo; W_hi], so that
+// x_lo W_hi + x_hi W_lo + x_hi W_hi accumulate with every product exact, correction blocks first (the tensor core truncates
+// its fp32 accumulator once per MMA), and bias / residual / old output / store are fp32.
+// Launch structure: programmatic dependent launch, with ConvArgs::pdl_mode letting the independent convolutions of a
+// lockstep AMP step start under their predecessor's tail.
+//
 // What the measurements behind this structure were (tools/umma_bench.cu, profiles/r1_umma_*):
 //   * one M=128 MMA costs max(N/2, ~40..50) cycles when issued from uniform registers, but ~124 when
 //     its descriptors are built in a divergent single-lane region (R2UR per operand) -> the issuer is
