@@ -106,7 +106,13 @@ inline UmmaTiling make_tiling(int ntaps, int Cin, int N, bool small = false, boo
   const int cin_pad = round_up_i(Cin, 16);
   if (cin_pad % 64 == 0) { t.KC = 8; t.NKB = cin_pad / 64; }
   else if (cin_pad <= 128) { t.KC = cin_pad / 8; t.NKB = 1; }
-  else { t.KC = 8; t.NKB = round_up_i(cin_pad, 64) / 64; }   // last k-block partly padding (zero weight rows; 3 x C of the split mode)
+  else {
+    // 3 x C of the split mode (144, 288 channels): 6-chunk k-blocks when they divide the channels exactly (no padded
+    // K-steps), else 8-chunk k-blocks with a partly padded last one (zero weight rows)
+    const int chunks = cin_pad / 8;
+    if (chunks % 6 == 0) { t.KC = 6; t.NKB = chunks / 6; }
+    else { t.KC = 8; t.NKB = round_up_i(cin_pad, 64) / 64; }
+  }
   // N tile: 256 columns by default -- a 128 x 256 x 16 MMA is the only cta_group::1 shape that runs at
   // the tensor-pipe floor (tools/umma_bench.cu) and it halves the A-tile re-reads per output column.
   static const int bnmax_env = [] { int v = env_int("BVG_CONV_BNMAX", 256); return (v == 128 || v == 192) ? v : 256; }();
