@@ -382,6 +382,10 @@ int build_tc32_image(bvg_handle* h, ConvLayer& L, float* w3, float absmax, cudaS
 
 int ensure_tc32_images(bvg_handle* h, cudaStream_t s) {
   if (h->tc32_ready) return 0;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(s, &cap) == cudaSuccess && cap != cudaStreamCaptureStatusNone)
+    return fail("fp32 tensor-core mode: the first forward of a handle builds the split weight images (allocation + synchronisation) "
+                "and cannot run inside a stream capture; run one eager forward first");
   std::vector<ConvLayer*> layers{&h->conv_pre};
   for (auto& L : h->ups) layers.push_back(&L);
   for (auto& L : h->c1) layers.push_back(&L);
