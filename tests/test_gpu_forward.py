@@ -656,12 +656,15 @@ for prec in ("bf16", "fp16"):
 np.savez(sys.argv[1], **out)
 '''
     res = {}
-    for v in ("0", "1"):
+    # "1": the default (lockstep, independent convolutions start under their predecessor's tail); "1c": lockstep with every
+    # launch chained (BVG_PDL_INDEP=0); "0": the sequential block order
+    for v, extra in (("0", {}), ("1", {}), ("1c", {"BVG_PDL_INDEP": "0"})):
         path = str(tmp_path / f"group{v}.npz")
-        env = dict(os.environ, BVG_ACT_GROUP=v)
+        env = dict(os.environ, BVG_ACT_GROUP=v[0], **extra)
         subprocess.run([sys.executable, "-c", code, path], check=True, env=env, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
                        timeout=600)
         res[v] = np.load(path)
     for prec in ("bf16", "fp16"):
         assert np.array_equal(res["0"][prec], res["1"][prec]), prec
+        assert np.array_equal(res["1c"][prec], res["1"][prec]), prec
         assert int(res["1"][prec + "_launches"]) == int(res["0"][prec + "_launches"]) - 72   # 6 stages x 6 steps x 2 launches saved
