@@ -561,6 +561,7 @@ int bvg_set_weight(bvg_handle* h, const char* name, const float* data, const int
   if (!is_device) CK(cudaStreamSynchronize((cudaStream_t)stream));
   s.set = true;
   h->finalized = false;
+  h->tc32_ready = false;   // the fp32 tensor-core images are rebuilt from the new weights by the next forward that needs them
   return 0;
 }
 

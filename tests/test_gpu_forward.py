@@ -668,3 +668,25 @@ np.savez(sys.argv[1], **out)
         assert np.array_equal(res["0"][prec], res["1"][prec]), prec
         assert np.array_equal(res["1c"][prec], res["1"][prec]), prec
         assert int(res["1"][prec + "_launches"]) == int(res["0"][prec + "_launches"]) - 72   # 6 stages x 6 steps x 2 launches saved
+
+
+def test_fp32tc_weight_reload_rebuilds_split_images():
+    """load_state_dict on a model that already decoded in the fp32 tensor-core mode: the split weight images are rebuilt from
+    the new weights (same handle), not reused."""
+    from b200vgan import synth
+    from b200vgan.model import BigVGAN
+    g = BigVGAN(dict(synth.H_DEFAULT), precision="fp32tc")
+    sd1 = synth.make_state_dict(1234, with_speaker_encoder=False)
+    sd2 = synth.make_state_dict(4321, with_speaker_encoder=False)
+    g.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd1.items()}, strict=False)
+    g = g.to("cuda")
+    g.remove_weight_norm()
+    g.eval()
+    x = synth.make_latents(6, 0, 1, 5)
+    emb = synth.make_speaker_embedding(B=1)
+    w1 = _run(g, x, emb, "fp32tc")
+    g.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd2.items()}, strict=False)
+    w2 = _run(g, x, emb, "fp32tc")
+    ref2 = _run(g, x, emb, "fp32")
+    assert np.abs(w2 - w1).max() > 1e-2            # other weights, other audio
+    assert np.abs(w2 - ref2).max() <= 5e-4         # and it is the new weights' audio
