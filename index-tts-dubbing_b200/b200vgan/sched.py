@@ -247,7 +247,7 @@ class LatentHandoff:
       * dtype    bf16 by default (what the bf16 mode stores anyway: bit-identical results to fp32 latents), fp16 / fp32 accepted;
       * stream   everything is ordered on torch's current stream -- no host synchronisation; a producer on another
                  stream records an event after its last write and the consumer stream waits on it (`wait_event`);
-      * graph    `decode(graph=True)` captures the whole ragged decode (pack -> 234 launches -> int16 PCM) for this
+      * graph    `decode(graph=True)` captures the whole ragged decode (pack -> 162 launches -> int16 PCM) for this
                  sentence geometry into a CUDA graph on first use and replays it afterwards: the buffers the graph
                  reads and writes are owned here, so their addresses never change (one launch per decode from the host).
     """
